@@ -1,0 +1,151 @@
+/*
+ * ngp_b200.h — C ABI of the B200-native (sm_100a) torch-ngp hot path.
+ *
+ * Plain pointers + sizes + a CUDA stream; no torch types.  All pointers are DEVICE
+ * pointers unless the name ends in _host.  Every function is asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and returns 0 on
+ * success or a non-zero NGP_E* code (message via ngp_last_error()).  The callee never
+ * allocates, frees or retains caller memory: the caller owns every buffer, exactly like
+ * the reference's pybind ABI (SURVEY §8b "Ownership").
+ *
+ * Each entry point replaces one function of the reference's native extension tables:
+ *   gridencoder/src/gridencoder.h:12-15   (bindings.cpp:6-8)
+ *   ffmlp/src/ffmlp.h:8-14                (bindings.cpp:6-10)
+ *   shencoder/src/shencoder.h:9-10        (bindings.cpp:6-7)
+ *   raymarching/src/raymarching.h:7-18    (bindings.cpp:7-18)
+ * Argument order and meaning follow those declarations; at::Tensor arguments become raw
+ * pointers, at::optional<Tensor> becomes a nullable pointer, and a trailing stream is
+ * added (the reference launches on the legacy default stream only).
+ */
+#ifndef NGP_B200_H
+#define NGP_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_OK            0
+#define NGP_EINVAL        1   /* unsupported template value / bad argument (reference: std::runtime_error) */
+#define NGP_ECUDA         2   /* CUDA launch / runtime error (reference: unchecked)                          */
+#define NGP_EUNSUPPORTED  3   /* feature outside the built configuration                                    */
+
+/* dtype codes for `void*` tensor arguments */
+#define NGP_F32 0
+#define NGP_F16 1
+
+typedef void* ngp_stream_t; /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char* ngp_last_error(void);        /* thread-local message of the last failing call       */
+int         ngp_version(void);           /* ABI version (this header: 1)                        */
+const char* ngp_build_arch(void);        /* "sm_100a"                                           */
+/* number of kernels launched by this library since load / last reset (bench `gpu_launches`)    */
+uint64_t    ngp_launch_count(void);
+void        ngp_reset_launch_count(void);
+
+/* ---- gridencoder  (gridencoder/src/gridencoder.h:12-15) ------------------------------------- */
+/* inputs [B,D] f32 in [0,1]; embeddings [sO,C] (dtype); offsets [L+1] i32;
+ * outputs: level_major!=0 -> [L,B,C] (reference-native layout, gridencoder.cu:388)
+ *          level_major==0 -> [B,L*C] (what grid.py:57 permutes to; the permute copy is fused away)
+ * dy_dx (nullable) [B,L,D,C].  S = log2(per_level_scale), H = base resolution. */
+int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                            void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L,
+                            float S, uint32_t H, void* dy_dx, uint32_t gridtype,
+                            int align_corners, uint32_t interp, int dtype, int level_major,
+                            ngp_stream_t stream);
+/* grad: level_major!=0 -> [L,B,C], else [B,L*C].  grad_embeddings [sO,C] must be zeroed by the
+ * caller (grid.py:77) and is accumulated with scatter-add.  grad_inputs (nullable) [B,D] (dtype),
+ * requires dy_dx. */
+int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                             const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, float S, uint32_t H, const void* dy_dx,
+                             void* grad_inputs, uint32_t gridtype, int align_corners,
+                             uint32_t interp, int dtype, int level_major, ngp_stream_t stream);
+/* gridencoder.h:15 — inputs [B,D] (dtype), adds weight * TV-gradient into `grad` in place. */
+int ngp_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                             const int32_t* offsets, float weight, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                             int align_corners, int dtype, ngp_stream_t stream);
+
+/* ---- shencoder  (shencoder/src/shencoder.h:9-10) -------------------------------------------- */
+/* inputs [B,3] f32; outputs [B,degree^2] f32; dy_dx (nullable) [B,3,degree^2] f32. */
+int ngp_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t D,
+                          uint32_t degree, float* dy_dx, ngp_stream_t stream);
+int ngp_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, uint32_t D,
+                           uint32_t degree, const float* dy_dx, float* grad_inputs,
+                           ngp_stream_t stream);
+
+/* ---- ffmlp  (ffmlp/src/ffmlp.h:8-14) ------------------------------------------------------- */
+/* All tensors fp16, row-major.  inputs [B,input_dim]; weights = [hidden,input_dim] then
+ * (num_layers-1) x [hidden,hidden] then [output_dim,hidden], each [out,in] row-major
+ * (ffmlp.cu:631-634).  B must be a multiple of 128 (ffmlp.py:157-159 pads).  hidden_dim == 64,
+ * input_dim in {16,32,48,64}, output_dim == 16 in this build; activation codes as
+ * ffmlp.py:89-96 (0 = ReLU ... 6 = None); output_activation must be 6 (ffmlp.py:108).
+ * forward_buffer [num_layers,B,hidden] receives every hidden activation (training). */
+int ngp_ffmlp_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim,
+                      uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                      uint32_t activation, uint32_t output_activation, void* forward_buffer,
+                      void* outputs, ngp_stream_t stream);
+/* inference_buffer is accepted for ABI parity (ffmlp.h:10) and never touched: activations stay
+ * in shared/tensor memory. */
+int ngp_ffmlp_inference(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim,
+                        uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                        uint32_t activation, uint32_t output_activation, void* inference_buffer,
+                        void* outputs, ngp_stream_t stream);
+/* grad [B,output_dim]; backward_buffer [num_layers,B,hidden] scratch (written: dL/d pre-activation,
+ * deepest layer first, as ffmlp.cu:749-895); grad_inputs [B,input_dim] iff calc_grad_inputs;
+ * grad_weights same layout as weights (fp16, overwritten).  workspace: at least
+ * ngp_ffmlp_backward_workspace_bytes() bytes of device scratch (fp32 partial weight grads). */
+size_t ngp_ffmlp_backward_workspace_bytes(uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                          uint32_t hidden_dim, uint32_t num_layers);
+int ngp_ffmlp_backward(const void* grad, const void* inputs, const void* weights,
+                       const void* forward_buffer, uint32_t B, uint32_t input_dim,
+                       uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                       uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
+                       void* backward_buffer, void* grad_inputs, void* grad_weights,
+                       void* workspace, size_t workspace_bytes, ngp_stream_t stream);
+/* ffmlp.h:13-14 — the reference (re)creates global side streams here; this build needs none. */
+int ngp_ffmlp_allocate_splitk(size_t size);
+int ngp_ffmlp_free_splitk(void);
+
+/* ---- raymarching  (raymarching/src/raymarching.h:7-18) -------------------------------------- */
+int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                           float min_near, float* nears, float* fars, ngp_stream_t stream);
+int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N,
+                     float* coords, ngp_stream_t stream);
+int ngp_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, ngp_stream_t stream);
+int ngp_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, ngp_stream_t stream);
+int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                 ngp_stream_t stream);
+/* rays [N,3] i32 = (ray id, offset, count); counter [2] i32 (points, rays) accumulated atomically.
+ * xyzs/dirs [M,3], deltas [M,2] must be zero-initialised by the caller (raymarching.py:205-207). */
+int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                         float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                         uint32_t M, const float* nears, const float* fars, float* xyzs,
+                         float* dirs, float* deltas, int32_t* rays, int32_t* counter,
+                         const float* noises, ngp_stream_t stream);
+int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                     const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                     float* weights_sum, float* depth, float* image,
+                                     ngp_stream_t stream);
+int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                      const float* sigmas, const float* rgbs, const float* deltas,
+                                      const int32_t* rays, const float* weights_sum,
+                                      const float* image, uint32_t M, uint32_t N, float T_thresh,
+                                      float* grad_sigmas, float* grad_rgbs, ngp_stream_t stream);
+int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
+                   const float* rays_t, const float* rays_o, const float* rays_d, float bound,
+                   float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
+                   const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                   const float* noises, ngp_stream_t stream);
+int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                       float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                       float* weights_sum, float* depth, float* image, ngp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H */

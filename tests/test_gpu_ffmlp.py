@@ -1,0 +1,179 @@
+"""GPU parity: tcgen05/TMEM fully-fused MLP (csrc/ffmlp.cu) vs the numpy oracle and the reference extension."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from util import gen, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _probe(mode):
+    import _ngp_b200 as nb
+    lib = nb.load()
+    lib.ngp_debug_umma.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_void_p]
+    lib.ngp_debug_umma.restype = ctypes.c_int
+    A = torch.randn(128, 64, generator=gen(1)).half().cuda()
+    Bm = torch.randn(64 if mode == 0 else 128, 64, generator=gen(2)).half().cuda()
+    D = torch.zeros(128 if mode == 0 else 64, 64, device="cuda")
+    rc = lib.ngp_debug_umma(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), mode, nb.stream())
+    assert rc == 0, lib.ngp_last_error()
+    torch.cuda.synchronize()
+    ref = A.float() @ Bm.float().T if mode == 0 else A.float().T @ Bm.float()
+    return D, ref
+
+
+def test_umma_kmajor_probe():
+    """One M=128,N=64,K=64 tcgen05.mma chain with 128B-swizzled K-major operands == A @ B^T (fp32 accumulate)."""
+    D, ref = _probe(0)
+    assert rel_err(D.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+def test_umma_mnmajor_probe():
+    """M=64,N=64 with both operands MN-major (contraction over 128 rows) == A^T @ B: the wgrad building block."""
+    D, ref = _probe(1)
+    assert rel_err(D.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+
+
+CFGS = [dict(input_dim=32, num_layers=2), dict(input_dim=32, num_layers=3), dict(input_dim=64, num_layers=2),
+        dict(input_dim=16, num_layers=4), dict(input_dim=48, num_layers=2)]
+
+
+def _mk(B, input_dim, num_layers, seed=0, scale=1.0):
+    n = 64 * (input_dim + 64 * (num_layers - 1) + 16)
+    std = np.sqrt(3 / 64)
+    w = ((torch.rand(n, generator=gen(seed)) * 2 - 1) * std).half()
+    x = (torch.randn(B, input_dim, generator=gen(seed + 1)) * scale).half()
+    return x, w
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("B", [128, 128 * 37])
+def test_forward_inference_vs_oracle(cfg, B):
+    """fp32-accumulate kernel vs fp32-accumulate numpy oracle: outputs agree to fp16 rounding (<= 2e-3 of the
+    output scale: one fp16 ulp at the top of the range; layer outputs may round differently by 1 ulp)."""
+    from oracle import oracle as O
+    from ffmlp.ffmlp import ffmlp_forward
+    x, w = _mk(B, **cfg)
+    y_ref, fwd_ref = O.mlp_forward(x.numpy(), w.numpy(), cfg["input_dim"], 64, cfg["num_layers"])
+    xd, wd = x.cuda(), w.cuda()
+    y_inf = ffmlp_forward(xd, wd, cfg["input_dim"], 16, 64, cfg["num_layers"], 0, 6, True, False)
+    assert rel_err(y_inf.cpu().numpy(), y_ref) < 2e-3
+    import _ngp_b200 as nb
+    fb = torch.empty(cfg["num_layers"], B, 64, dtype=torch.half, device="cuda"); y = torch.empty(B, 16, dtype=torch.half, device="cuda")
+    nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), B, cfg["input_dim"], 16, 64, cfg["num_layers"], 0, 6, fb.data_ptr(), y.data_ptr())
+    assert torch.equal(y, y_inf)                               # training and inference kernels agree bit-for-bit
+    assert rel_err(fb.cpu().numpy(), fwd_ref) < 2e-3
+    assert (fb >= 0).all()
+
+
+@pytest.mark.parametrize("act", [0, 1, 3, 4, 5, 6])
+def test_activations(act):
+    from oracle import oracle as O
+    import _ngp_b200 as nb
+    x, w = _mk(256, 32, 2, scale=0.5)
+    y_ref, fwd_ref = O.mlp_forward(x.numpy(), w.numpy(), 32, 64, 2, activation=act)
+    xd, wd = x.cuda(), w.cuda()
+    fb = torch.empty(2, 256, 64, dtype=torch.half, device="cuda"); y = torch.empty(256, 16, dtype=torch.half, device="cuda")
+    nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), 256, 32, 16, 64, 2, act, 6, fb.data_ptr(), y.data_ptr())
+    assert rel_err(y.cpu().numpy(), y_ref) < 3e-3 and rel_err(fb.cpu().numpy(), fwd_ref) < 3e-3
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+def test_backward_vs_oracle(cfg):
+    from oracle import oracle as O
+    import _ngp_b200 as nb
+    B = 128 * 9
+    x, w = _mk(B, **cfg)
+    nl, ind = cfg["num_layers"], cfg["input_dim"]
+    y_ref, fwd_ref = O.mlp_forward(x.numpy(), w.numpy(), ind, 64, nl)
+    g = (torch.randn(B, 16, generator=gen(5)) * 0.1).half()
+    gi_ref, gw_ref, bb_ref = O.mlp_backward(g.numpy(), x.numpy(), w.numpy(), fwd_ref, ind, 64, nl)
+    xd, wd, gd = x.cuda(), w.cuda(), g.cuda()
+    fb = torch.from_numpy(fwd_ref).cuda()   # feed the oracle's activations so both sides mask identically
+    bb = torch.zeros(nl, B, 64, dtype=torch.half, device="cuda"); gi = torch.zeros(B, ind, dtype=torch.half, device="cuda")
+    gw = torch.zeros_like(wd)
+    nbytes = nb.load().ngp_ffmlp_backward_workspace_bytes(B, ind, 16, 64, nl)
+    ws = torch.empty(nbytes // 4, device="cuda")
+    nb.call("ngp_ffmlp_backward", gd.data_ptr(), xd.data_ptr(), wd.data_ptr(), fb.data_ptr(), B, ind, 16, 64, nl, 0, 6, 1,
+            bb.data_ptr(), gi.data_ptr(), gw.data_ptr(), ws.data_ptr(), nbytes)
+    assert rel_err(bb.cpu().numpy(), bb_ref) < 2e-3
+    assert rel_err(gi.cpu().numpy(), gi_ref) < 2e-3
+    assert rel_err(gw.float().cpu().numpy(), gw_ref) < 2e-3
+    # the fp32 workspace holds the unrounded weight gradient
+    assert rel_err(ws.cpu().numpy(), gw_ref) < 1e-3
+
+
+def test_module_autograd_matches_torch_mlp():
+    """FFMLP module (pad-128 rule, autocast, seed-42 init) vs the reference's own nn.Linear restatement
+    (testing/test_ffmlp.py:11-43) in fp32: 1e-3 of the output scale (north_star tolerance)."""
+    from ffmlp import FFMLP
+    mlp = FFMLP(32, 3, 64, 3).cuda().train()
+    assert mlp.weights.shape == (64 * (32 + 64 * 2 + 16),)
+    W = mlp.weights.detach().float()
+    mats = [W[:64 * 32].view(64, 32), W[2048:2048 + 4096].view(64, 64), W[2048 + 4096:2048 + 8192].view(64, 64),
+            W[2048 + 8192:].view(16, 64)]
+    x = (torch.randn(1000, 32, generator=gen(3)) * 0.5).cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = mlp(x)
+    assert y.shape == (1000, 3) and y.dtype == torch.float16
+    g = torch.randn(1000, 3, generator=gen(4)).cuda()
+    y.float().backward(g)
+    xr = x.detach().half().float().requires_grad_(True)
+    mr = [m.half().float().requires_grad_(True) for m in mats]
+    h = xr
+    for m in mr[:-1]:
+        h = torch.relu(h @ m.T)
+    yr = (h @ mr[-1].T)[:, :3]
+    yr.backward(g)
+    assert rel_err(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy()) < 2e-3
+    assert rel_err(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 3e-3
+    gw_ref = torch.cat([m.grad.reshape(-1) for m in mr])
+    assert rel_err(mlp.weights.grad.cpu().numpy(), gw_ref.cpu().numpy()) < 3e-3
+    # eval() -> inference kernel, same numbers
+    mlp.eval()
+    with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():
+        y2 = mlp(x.detach())
+    assert torch.equal(y2, y.detach())
+
+
+def test_vs_reference_extension():
+    """Against the reference's wmma/CUTLASS kernels (fp16 accumulate): 1e-3-level agreement of outputs; the
+    reference's own fp16 split-K makes its weight gradients the noisier side (bounded at 2e-2)."""
+    from oracle import ref_driver as R
+    if not R.available("ffmlp"):
+        pytest.skip("oracle/_ref/ffmlp not built")
+    import _ngp_b200 as nb
+    B = 128 * 64
+    for cfg in (dict(input_dim=32, num_layers=2), dict(input_dim=32, num_layers=3)):
+        x, w = _mk(B, **cfg)
+        xd, wd = x.cuda(), w.cuda()
+        nl, ind = cfg["num_layers"], cfg["input_dim"]
+        yr, fbr = R.ffmlp_forward(xd, wd, ind, 16, 64, nl)
+        fb = torch.empty_like(fbr); y = torch.empty_like(yr)
+        nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), B, ind, 16, 64, nl, 0, 6, fb.data_ptr(), y.data_ptr())
+        assert rel_err(y.cpu().numpy(), yr.cpu().numpy()) < 3e-3
+        assert rel_err(fb.cpu().numpy(), fbr.cpu().numpy()) < 3e-3
+        g = (torch.randn(B, 16, generator=gen(5)) * 0.01).half().cuda()
+        gir, gwr, bbr = R.ffmlp_backward(g, xd, wd, fbr, ind, 16, 64, nl)
+        torch.cuda.synchronize()
+        bb = torch.zeros_like(bbr); gi = torch.zeros_like(xd); gw = torch.zeros_like(wd)
+        nbytes = nb.load().ngp_ffmlp_backward_workspace_bytes(B, ind, 16, 64, nl)
+        ws = torch.empty(nbytes // 4, device="cuda")
+        nb.call("ngp_ffmlp_backward", g.data_ptr(), xd.data_ptr(), wd.data_ptr(), fbr.data_ptr(), B, ind, 16, 64, nl, 0, 6, 1,
+                bb.data_ptr(), gi.data_ptr(), gw.data_ptr(), ws.data_ptr(), nbytes)
+        assert rel_err(bb.cpu().numpy(), bbr.cpu().numpy()) < 5e-3
+        assert rel_err(gi.cpu().numpy(), gir.cpu().numpy()) < 5e-3
+        assert rel_err(gw.float().cpu().numpy(), gwr.float().cpu().numpy()) < 2e-2
+
+
+def test_errors():
+    from ffmlp.ffmlp import ffmlp_forward
+    x, w = _mk(100, 32, 2)
+    with pytest.raises(RuntimeError):
+        ffmlp_forward(x.cuda(), w.cuda(), 32, 16, 64, 2, 0, 6, True, False)       # B % 128 != 0
+    x, w = _mk(128, 32, 2)
+    with pytest.raises(RuntimeError):
+        ffmlp_forward(x.cuda(), w.cuda(), 32, 16, 128, 2, 0, 6, True, False)      # hidden 128: not in this build

@@ -1,0 +1,102 @@
+"""ctypes binding of libngp_b200.so — the C-ABI declared in include/ngp_b200.h.
+
+This is the only place the host-side packages (gridencoder, ffmlp, shencoder, raymarching) touch
+native code.  There is NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference raises RuntimeError from its extensions as well, SURVEY §8b "Errors").
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libngp_b200.so")
+
+_c = ctypes
+_vp, _u32, _i32, _f32, _sz = _c.c_void_p, _c.c_uint32, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> argtypes, in include/ngp_b200.h order
+_SIGNATURES = {
+    "ngp_grid_encode_forward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _u32, _i32, _u32, _i32, _i32, _vp],
+    "ngp_grid_encode_backward": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _vp, _u32, _i32, _u32, _i32, _i32, _vp],
+    "ngp_grad_total_variation": [_vp, _vp, _vp, _vp, _f32, _u32, _u32, _u32, _u32, _f32, _u32, _u32, _i32, _i32, _vp],
+    "ngp_grid_level_scales": [_vp, _u32, _f32, _u32, _vp],
+    "ngp_sh_encode_forward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
+    "ngp_sh_encode_backward": [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
+    "ngp_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "ngp_ffmlp_inference": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
+    "ngp_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _sz, _vp],
+    "ngp_ffmlp_allocate_splitk": [_sz],
+    "ngp_ffmlp_free_splitk": [],
+    "ngp_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
+    "ngp_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
+    "ngp_morton3D": [_vp, _u32, _vp, _vp],
+    "ngp_morton3D_invert": [_vp, _u32, _vp, _vp],
+    "ngp_packbits": [_vp, _u32, _f32, _vp, _vp],
+    "ngp_march_rays_train": [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_composite_rays_train_forward": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp],
+    "ngp_composite_rays_train_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp],
+    "ngp_march_rays": [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+}
+# every symbol include/ngp_b200.h declares (tests check the .so exports all of them)
+EXPORTED = sorted(list(_SIGNATURES) + ["ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
+                                       "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes"])
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises RuntimeError if the .so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libngp_b200.so not found at {LIB_PATH}: build it with `python torch-ngp_b200/build.py` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = _c.c_int
+    lib.ngp_last_error.restype = _c.c_char_p
+    lib.ngp_build_arch.restype = _c.c_char_p
+    lib.ngp_version.restype = _c.c_int
+    lib.ngp_launch_count.restype = _c.c_uint64
+    lib.ngp_reset_launch_count.restype = None
+    lib.ngp_ffmlp_backward_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32, _u32]
+    lib.ngp_ffmlp_backward_workspace_bytes.restype = _sz
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on the current stream; raise RuntimeError on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.ngp_last_error().decode()}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ngp_b200: expected a CUDA tensor (this build has no CPU path)")
+
+
+def launch_count():
+    return int(load().ngp_launch_count())
+
+
+def reset_launch_count():
+    load().ngp_reset_launch_count()

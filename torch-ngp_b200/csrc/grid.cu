@@ -1,0 +1,561 @@
+// grid.cu — multiresolution hash/tiled grid encoding for sm_100a.
+//
+// Replaces the reference's gridencoder/src/gridencoder.cu (kernel_grid :87-245,
+// kernel_grid_backward :248-340, kernel_input_backward :343-369, kernel_grad_tv :506-610).
+// Arithmetic contract kept from the reference:
+//   * level scale   = fma(exp2f(level*S), H, -1)           (gridencoder.cu:138)
+//   * pos           = fma(x, scale, align ? 0 : 0.5)        (:148)  -> floorf -> frac
+//   * corner index  = dense sum while stride <= hashmap_size, else xor-prime hash (:50-84)
+//   * fp16 tables   : per-corner product rounded to fp16, then fp16 running sum (:164,187)
+//   * fp32 tables   : fused multiply-add running sum
+// What is different (B200-first):
+//   * one CTA owns a tile of 32 points x all L levels (warp = level, lane = point) so the
+//     [B, L*C] feature row is assembled in shared memory and leaves the SM as full 128-bit
+//     coalesced stores — the reference's [L,B,C] write + permute copy (grid.py:57) is gone,
+//   * the backward reads dL/dy straight from [B, L*C] (no permute copy, grid.py:75) and scatters
+//     with red.global.add.noftz.f16x2 / red.global.add.v2.f32 (no return value, one op per corner),
+//   * everything runs on the caller's stream.
+#include "common.cuh"
+
+namespace ngp {
+
+static constexpr uint32_t TILE_PTS = 32;   // points per CTA tile == warp width
+
+__device__ __forceinline__ float smoothstep_f(float v) { return v * v * (3.0f - 2.0f * v); }
+__device__ __forceinline__ float smoothstep_df(float v) { return 6 * v * (1.0f - v); }
+
+// xor-prime spatial hash (instant-ngp's published primes; gridencoder.cu:50-63)
+template <uint32_t D>
+__device__ __forceinline__ uint32_t hash_coords(const uint32_t p[D]) {
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u,
+                                    2097192037u, 1434869437u, 2165219737u};
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < D; ++i) r ^= p[i] * primes[i];
+    return r;
+}
+
+// entry index inside one level (gridencoder.cu:66-84); returned WITHOUT the *C+ch.
+template <uint32_t D>
+__device__ __forceinline__ uint32_t level_index(uint32_t gridtype, bool align_corners,
+                                                uint32_t hashmap_size, uint32_t resolution,
+                                                const uint32_t p[D]) {
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        if (stride <= hashmap_size) {
+            index += p[d] * stride;
+            stride *= align_corners ? resolution : (resolution + 1);
+        }
+    }
+    if (gridtype == 0 && stride > hashmap_size) index = hash_coords<D>(p);
+    return index % hashmap_size;
+}
+
+__device__ __forceinline__ float level_scale(uint32_t level, float S, uint32_t H) {
+    return fmaf(exp2f(level * S), (float)H, -1.0f);
+}
+
+// ---- accumulate / load / store helpers per table dtype --------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ void acc(float& r, float w, float g) { r = fmaf(w, g, r); }
+__device__ __forceinline__ void acc(__half& r, float w, __half g) {
+    const __half p = __float2half_rn(w * __half2float(g));
+    r = __float2half_rn(__half2float(r) + __half2float(p));
+}
+
+// vector load of the C features of one table entry
+template <typename T, uint32_t C>
+__device__ __forceinline__ void load_entry(const T* __restrict__ p, T out[C]) {
+    if constexpr (sizeof(T) * C == 4) {
+        uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+        *reinterpret_cast<uint32_t*>(out) = v;
+    } else if constexpr (sizeof(T) * C == 8) {
+        uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        *reinterpret_cast<uint2*>(out) = v;
+    } else if constexpr (sizeof(T) * C == 16) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        *reinterpret_cast<uint4*>(out) = v;
+    } else if constexpr (sizeof(T) * C == 32) {
+        uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p));
+        uint4 v1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        reinterpret_cast<uint4*>(out)[0] = v0;
+        reinterpret_cast<uint4*>(out)[1] = v1;
+    } else {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) out[c] = p[c];
+    }
+}
+
+// ============================== forward ======================================================
+// grid: ceil(B / 32) CTAs; block: 32 x NW threads (NW = min(L, 16) warps); warp w walks levels
+// w, w+NW, ...; lane = point.  Dynamic smem: 32 * L * C * sizeof(T) (feature tile).
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(512)
+k_grid_forward(const float* __restrict__ inputs, const T* __restrict__ table,
+               const int* __restrict__ offsets, T* __restrict__ outputs, const uint32_t B,
+               const uint32_t L, const float S, const uint32_t H, T* __restrict__ dy_dx,
+               const uint32_t gridtype, const bool align_corners, const uint32_t interp,
+               const bool level_major) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);            // [32][pitch] (odd word pitch: conflict-free)
+    const uint32_t lane = threadIdx.x;
+    const uint32_t warp = threadIdx.y;
+    const uint32_t nwarp = blockDim.y;
+    const uint32_t b0 = blockIdx.x * TILE_PTS;
+    const uint32_t b = b0 + lane;
+    const bool valid = b < B;
+    const uint32_t F = L * C;
+    // row pitch of the staging tile: an odd number of 32-bit words so that the 32 lanes of a warp
+    // (same level, consecutive points) hit 32 different banks.
+    const bool word_rows = (F * sizeof(T)) % 4 == 0;
+    const uint32_t row_words = (F * (uint32_t)sizeof(T)) / 4;
+    const uint32_t pitch_words = row_words | 1u;
+    const uint32_t pitchE = word_rows ? pitch_words * 4 / (uint32_t)sizeof(T) : F;
+
+    float x[D];
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        x[d] = valid ? __ldg(inputs + (size_t)b * D + d) : 0.f;
+        if (x[d] < 0 || x[d] > 1) oob = true;
+    }
+
+    for (uint32_t level = warp; level < L; level += nwarp) {
+        T res[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) res[c] = from_f<T>(0.f);
+
+        if (valid) {
+            const uint32_t off = (uint32_t)__ldg(offsets + level);
+            const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+            const float scale = level_scale(level, S, H);
+            const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+            const T* __restrict__ lvl = table + (size_t)off * C;
+
+            float pos[D], pos_deriv[D];
+            uint32_t pg[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
+                const float fl = floorf(pos[d]);
+                pg[d] = (uint32_t)fl;
+                pos[d] -= (float)pg[d];
+                if (interp == 1) {
+                    pos_deriv[d] = smoothstep_df(pos[d]);
+                    pos[d] = smoothstep_f(pos[d]);
+                } else {
+                    pos_deriv[d] = 1.0f;
+                }
+            }
+
+            if (!oob) {
+                // issue all 2^D gathers first (memory-level parallelism), then blend in the
+                // reference's corner order (idx bit d selects +1 along dim d).
+                T val[1 << D][C];
+                float wgt[1 << D];
+#pragma unroll
+                for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+                    float w = 1;
+                    uint32_t pl[D];
+#pragma unroll
+                    for (uint32_t d = 0; d < D; ++d) {
+                        if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                        else                        { w *= pos[d];     pl[d] = pg[d] + 1; }
+                    }
+                    wgt[idx] = w;
+                    const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+                    load_entry<T, C>(lvl + (size_t)index * C, val[idx]);
+                }
+#pragma unroll
+                for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) acc(res[c], wgt[idx], val[idx][c]);
+                }
+
+                if (dy_dx) {
+                    T* __restrict__ dst = dy_dx + (size_t)b * D * F + (size_t)level * D * C;  // [B,L,D,C]
+#pragma unroll
+                    for (uint32_t gd = 0; gd < D; ++gd) {
+                        T rg[C];
+#pragma unroll
+                        for (uint32_t c = 0; c < C; ++c) rg[c] = from_f<T>(0.f);
+#pragma unroll
+                        for (uint32_t idx = 0; idx < (1u << (D - 1)); ++idx) {
+                            float w = scale;
+                            uint32_t pl[D];
+#pragma unroll
+                            for (uint32_t nd = 0; nd < D - 1; ++nd) {
+                                const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                                if ((idx & (1u << nd)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                                else                         { w *= pos[d];     pl[d] = pg[d] + 1; }
+                            }
+                            pl[gd] = pg[gd];
+                            const uint32_t il = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+                            pl[gd] = pg[gd] + 1;
+                            const uint32_t ir = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+                            T vl[C], vr[C];
+                            load_entry<T, C>(lvl + (size_t)il * C, vl);
+                            load_entry<T, C>(lvl + (size_t)ir * C, vr);
+#pragma unroll
+                            for (uint32_t c = 0; c < C; ++c) {
+                                // (right - left) is formed in table precision, as the reference does
+                                const T diff = from_f<T>(to_f(vr[c]) - to_f(vl[c]));
+                                if constexpr (sizeof(T) == 4) {
+                                    rg[c] = fmaf(w * to_f(diff), pos_deriv[gd], rg[c]);
+                                } else {
+                                    const T p = from_f<T>(w * to_f(diff) * pos_deriv[gd]);
+                                    rg[c] = from_f<T>(to_f(rg[c]) + to_f(p));
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (uint32_t c = 0; c < C; ++c) dst[gd * C + c] = rg[c];
+                    }
+                }
+            } else if (dy_dx) {
+                T* __restrict__ dst = dy_dx + (size_t)b * D * F + (size_t)level * D * C;
+#pragma unroll
+                for (uint32_t i = 0; i < D * C; ++i) dst[i] = from_f<T>(0.f);
+            }
+        }
+
+        if (level_major) {
+            if (valid) {
+                T* __restrict__ dst = outputs + ((size_t)level * B + b) * C;
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) dst[c] = res[c];
+            }
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) tile[lane * pitchE + level * C + c] = res[c];
+        }
+    }
+
+    if (!level_major) {
+        __syncthreads();
+        // the tile [32][F] is one contiguous span of the [B, F] output
+        const uint32_t npts = min(TILE_PTS, B - b0);
+        const size_t base = (size_t)b0 * F;
+        const uint32_t nelem = npts * F;
+        const uint32_t tid = threadIdx.y * 32 + threadIdx.x;
+        const uint32_t nthr = blockDim.y * 32;
+        if (word_rows) {
+            // 32 lanes x 4 B = one full 128-byte line per warp store
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(tile);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(outputs + base);
+            const uint32_t nwords = npts * row_words;
+            for (uint32_t i = tid; i < nwords; i += nthr) {
+                const uint32_t r = i / row_words, wd = i - r * row_words;
+                dst[i] = src[r * pitch_words + wd];
+            }
+        } else {
+            for (uint32_t i = tid; i < nelem; i += nthr) outputs[base + i] = tile[i];
+        }
+    }
+}
+
+// ============================== backward =====================================================
+__device__ __forceinline__ void red_add_h2(__half* addr, __half2 v) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&v);
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" ::"l"(addr), "r"(u) : "memory");
+}
+__device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_f1(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
+}
+
+// same tiling as the forward: warp = level, lane = point.  grad is [B, L*C] (or [L,B,C]).
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(512)
+k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
+                const int* __restrict__ offsets, T* __restrict__ grad_table, const uint32_t B,
+                const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
+                const bool align_corners, const uint32_t interp, const bool level_major) {
+    const uint32_t lane = threadIdx.x;
+    const uint32_t warp = threadIdx.y;
+    const uint32_t nwarp = blockDim.y;
+    const uint32_t b = blockIdx.x * TILE_PTS + lane;
+    if (b >= B) return;
+    const uint32_t F = L * C;
+
+    float x[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        x[d] = __ldg(inputs + (size_t)b * D + d);
+        if (x[d] < 0 || x[d] > 1) return;   // grad_table starts at zero (gridencoder.cu:284-289)
+    }
+
+    for (uint32_t level = warp; level < L; level += nwarp) {
+        const uint32_t off = (uint32_t)__ldg(offsets + level);
+        const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
+        const float scale = level_scale(level, S, H);
+        const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+        T* __restrict__ lvl = grad_table + (size_t)off * C;
+
+        T g[C];
+        const T* __restrict__ gsrc = level_major ? grad + ((size_t)level * B + b) * C
+                                                 : grad + (size_t)b * F + (size_t)level * C;
+        load_entry<T, C>(gsrc, g);
+
+        float pos[D];
+        uint32_t pg[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+            pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
+            pg[d] = (uint32_t)floorf(pos[d]);
+            pos[d] -= (float)pg[d];
+            if (interp == 1) pos[d] = smoothstep_f(pos[d]);
+        }
+
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            float w = 1;
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
+                else                        { w *= pos[d];     pl[d] = pg[d] + 1; }
+            }
+            const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+            T* dst = lvl + (size_t)index * C;
+            if constexpr (sizeof(T) == 2 && (C % 2 == 0)) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c += 2) {
+                    __half2 v;
+                    v.x = __float2half_rn(w * __half2float(g[c]));
+                    v.y = __float2half_rn(w * __half2float(g[c + 1]));
+                    red_add_h2(reinterpret_cast<__half*>(dst + c), v);
+                }
+            } else if constexpr (sizeof(T) == 2) {
+                // C == 1 half: scalar f16 reduction (the reference's path for this case is a stub)
+                atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(w * __half2float(g[0])));
+            } else if constexpr (C % 2 == 0) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c += 2)
+                    red_add_f2(reinterpret_cast<float*>(dst + c), w * to_f(g[c]), w * to_f(g[c + 1]));
+            } else {
+                red_add_f1(reinterpret_cast<float*>(dst), w * to_f(g[0]));
+            }
+        }
+    }
+}
+
+// dL/dx = sum_{l,c} dL/dy * dy_dx   (gridencoder.cu:343-369); one thread per (point, dim)
+template <typename T, uint32_t D, uint32_t C>
+__global__ void k_grid_input_backward(const T* __restrict__ grad, const T* __restrict__ dy_dx,
+                                      T* __restrict__ grad_inputs, uint32_t B, uint32_t L,
+                                      const bool level_major) {
+    const uint32_t t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const uint32_t F = L * C;
+    const T* __restrict__ dd = dy_dx + (size_t)b * L * D * C;
+    T result = from_f<T>(0.f);
+    for (uint32_t l = 0; l < L; ++l) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) {
+            const T gv = level_major ? grad[((size_t)l * B + b) * C + c] : grad[(size_t)b * F + l * C + c];
+            const T dv = dd[l * D * C + d * C + c];
+            if constexpr (sizeof(T) == 4) {
+                result = fmaf(to_f(gv), to_f(dv), result);
+            } else {
+                const T p = from_f<T>(to_f(gv) * to_f(dv));
+                result = from_f<T>(to_f(result) + to_f(p));
+            }
+        }
+    }
+    grad_inputs[t] = result;
+}
+
+// total-variation gradient (gridencoder.cu:506-610); cold path, thread per (point, level)
+template <typename T, uint32_t D, uint32_t C>
+__global__ void k_grid_grad_tv(const T* __restrict__ inputs, const T* __restrict__ table,
+                               T* __restrict__ grad, const int* __restrict__ offsets,
+                               const float weight, const uint32_t B, const uint32_t L, const float S,
+                               const uint32_t H, const uint32_t gridtype, const bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const uint32_t off = (uint32_t)offsets[level];
+    const T* __restrict__ lvl = table + (size_t)off * C;
+    T* __restrict__ glvl = grad + (size_t)off * C;
+
+    float x[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        x[d] = to_f(inputs[(size_t)b * D + d]);
+        if (x[d] < 0 || x[d] > 1) return;
+    }
+    const uint32_t hashmap_size = (uint32_t)offsets[level + 1] - off;
+    const float scale = level_scale(level, S, H);
+    const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
+
+    uint32_t pg[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) pg[d] = (uint32_t)floorf(fmaf(x[d], scale, align_corners ? 0.0f : 0.5f));
+
+    float results[C], idelta[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) { results[c] = 0.f; idelta[c] = 0.f; }
+    const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pg);
+    const float w = weight / (2 * D);
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        const uint32_t cur = pg[d];
+        if (cur < resolution) {
+            pg[d] = cur + 1;
+            const uint32_t ir = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pg);
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                const float gv = to_f(lvl[(size_t)index * C + c]) - to_f(lvl[(size_t)ir * C + c]);
+                results[c] += gv; idelta[c] += gv * gv;
+            }
+        }
+        if (cur > 0) {
+            pg[d] = cur - 1;
+            const uint32_t il = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pg);
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                const float gv = to_f(lvl[(size_t)index * C + c]) - to_f(lvl[(size_t)il * C + c]);
+                results[c] += gv; idelta[c] += gv * gv;
+            }
+        }
+        pg[d] = cur;
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) {
+        const float v = w * results[c] * rsqrtf(idelta[c] + 1e-9f);
+        if constexpr (sizeof(T) == 4) atomicAdd(reinterpret_cast<float*>(glvl + (size_t)index * C + c), v);
+        else atomicAdd(reinterpret_cast<__half*>(glvl + (size_t)index * C + c), __float2half_rn(v));
+    }
+}
+
+// per-level scale table as computed on the device (test hook: lets the CPU oracle use the exact
+// ex2.approx-based values the kernels use; see oracle/ngp_oracle.c grid_level_scale()).
+__global__ void k_level_scales(float* out, uint32_t L, float S, uint32_t H) {
+    const uint32_t l = threadIdx.x;
+    if (l < L) out[l] = level_scale(l, S, H);
+}
+
+// ---- dispatch -------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C>
+static int launch_fwd(const float* inputs, const void* emb, const int* offsets, void* out, uint32_t B,
+                      uint32_t L, float S, uint32_t H, void* dy_dx, uint32_t gridtype, bool ac,
+                      uint32_t interp, bool level_major, cudaStream_t st) {
+    const uint32_t nw = L < 16 ? L : 16;
+    dim3 block(32, nw);
+    dim3 grid(div_up(B, TILE_PTS));
+    size_t smem = level_major ? 0 : (size_t)TILE_PTS * ((((size_t)L * C * sizeof(T)) / 4 | 1) * 4 + 4);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_grid_forward<T, D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(NGP_EINVAL, "grid_encode_forward: L*C too large for shared memory");
+    }
+    k_grid_forward<T, D, C><<<grid, block, smem, st>>>(inputs, (const T*)emb, offsets, (T*)out, B, L, S, H,
+                                                      (T*)dy_dx, gridtype, ac, interp, level_major);
+    return check_launch("grid_encode_forward");
+}
+
+template <typename T, uint32_t D, uint32_t C>
+static int launch_bwd(const void* grad, const float* inputs, const int* offsets, void* gemb, uint32_t B,
+                      uint32_t L, float S, uint32_t H, const void* dy_dx, void* ginp, uint32_t gridtype,
+                      bool ac, uint32_t interp, bool level_major, cudaStream_t st) {
+    const uint32_t nw = L < 16 ? L : 16;
+    dim3 block(32, nw);
+    dim3 grid(div_up(B, TILE_PTS));
+    k_grid_backward<T, D, C><<<grid, block, 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
+                                                     gridtype, ac, interp, level_major);
+    int rc = check_launch("grid_encode_backward");
+    if (rc) return rc;
+    if (dy_dx && ginp) {
+        k_grid_input_backward<T, D, C><<<div_up(B * D, 256u), 256, 0, st>>>((const T*)grad, (const T*)dy_dx,
+                                                                            (T*)ginp, B, L, level_major);
+        rc = check_launch("grid_encode_backward(input)");
+    }
+    return rc;
+}
+
+template <typename T, uint32_t D, uint32_t C>
+static int launch_tv(const void* inputs, const void* emb, void* grad, const int* offsets, float weight,
+                     uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    dim3 grid(div_up(B, 512u), L);
+    k_grid_grad_tv<T, D, C><<<grid, 512, 0, st>>>((const T*)inputs, (const T*)emb, (T*)grad, offsets, weight,
+                                                 B, L, S, H, gridtype, ac);
+    return check_launch("grad_total_variation");
+}
+
+#define NGP_DISPATCH_DC(FN, T, ...)                                                             \
+    switch (D * 16 + C) {                                                                       \
+        case 2 * 16 + 1: return FN<T, 2, 1>(__VA_ARGS__);                                       \
+        case 2 * 16 + 2: return FN<T, 2, 2>(__VA_ARGS__);                                       \
+        case 2 * 16 + 4: return FN<T, 2, 4>(__VA_ARGS__);                                       \
+        case 2 * 16 + 8: return FN<T, 2, 8>(__VA_ARGS__);                                       \
+        case 3 * 16 + 1: return FN<T, 3, 1>(__VA_ARGS__);                                       \
+        case 3 * 16 + 2: return FN<T, 3, 2>(__VA_ARGS__);                                       \
+        case 3 * 16 + 4: return FN<T, 3, 4>(__VA_ARGS__);                                       \
+        case 3 * 16 + 8: return FN<T, 3, 8>(__VA_ARGS__);                                       \
+        case 4 * 16 + 1: return FN<T, 4, 1>(__VA_ARGS__);                                       \
+        case 4 * 16 + 2: return FN<T, 4, 2>(__VA_ARGS__);                                       \
+        case 4 * 16 + 4: return FN<T, 4, 4>(__VA_ARGS__);                                       \
+        case 4 * 16 + 8: return FN<T, 4, 8>(__VA_ARGS__);                                       \
+        case 5 * 16 + 1: return FN<T, 5, 1>(__VA_ARGS__);                                       \
+        case 5 * 16 + 2: return FN<T, 5, 2>(__VA_ARGS__);                                       \
+        case 5 * 16 + 4: return FN<T, 5, 4>(__VA_ARGS__);                                       \
+        case 5 * 16 + 8: return FN<T, 5, 8>(__VA_ARGS__);                                       \
+        default: return fail(NGP_EINVAL, "GridEncoding: D must be 2..5 and C must be 1, 2, 4, or 8 (got D=%u C=%u)", D, C); \
+    }
+
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets,
+                                       void* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                       uint32_t H, void* dy_dx, uint32_t gridtype, int align_corners,
+                                       uint32_t interp, int dtype, int level_major, ngp_stream_t stream) {
+    if (B == 0) return NGP_OK;
+    if (!inputs || !embeddings || !offsets || !outputs) return fail(NGP_EINVAL, "grid_encode_forward: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (dtype == NGP_F16) { NGP_DISPATCH_DC(launch_fwd, __half, inputs, embeddings, offsets, outputs, B, L, S, H, dy_dx, gridtype, align_corners != 0, interp, level_major != 0, st) }
+    if (dtype == NGP_F32) { NGP_DISPATCH_DC(launch_fwd, float, inputs, embeddings, offsets, outputs, B, L, S, H, dy_dx, gridtype, align_corners != 0, interp, level_major != 0, st) }
+    return fail(NGP_EINVAL, "grid_encode_forward: dtype must be NGP_F32 or NGP_F16");
+}
+
+extern "C" int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                        const int32_t* offsets, void* grad_embeddings, uint32_t B, uint32_t D,
+                                        uint32_t C, uint32_t L, float S, uint32_t H, const void* dy_dx,
+                                        void* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                        int dtype, int level_major, ngp_stream_t stream) {
+    (void)embeddings;
+    if (B == 0) return NGP_OK;
+    if (!grad || !inputs || !offsets || !grad_embeddings) return fail(NGP_EINVAL, "grid_encode_backward: null pointer");
+    cudaStream_t st = as_stream(stream);
+    if (dtype == NGP_F16) { NGP_DISPATCH_DC(launch_bwd, __half, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs, gridtype, align_corners != 0, interp, level_major != 0, st) }
+    if (dtype == NGP_F32) { NGP_DISPATCH_DC(launch_bwd, float, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs, gridtype, align_corners != 0, interp, level_major != 0, st) }
+    return fail(NGP_EINVAL, "grid_encode_backward: dtype must be NGP_F32 or NGP_F16");
+}
+
+extern "C" int ngp_grad_total_variation(const void* inputs, const void* embeddings, void* grad,
+                                        const int32_t* offsets, float weight, uint32_t B, uint32_t D, uint32_t C,
+                                        uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                        int dtype, ngp_stream_t stream) {
+    if (B == 0) return NGP_OK;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == NGP_F16) { NGP_DISPATCH_DC(launch_tv, __half, inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, align_corners != 0, st) }
+    if (dtype == NGP_F32) { NGP_DISPATCH_DC(launch_tv, float, inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, align_corners != 0, st) }
+    return fail(NGP_EINVAL, "grad_total_variation: dtype must be NGP_F32 or NGP_F16");
+}
+
+// test hook (not part of the reference ABI): device-computed per-level scales
+extern "C" int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream) {
+    if (L > 1024) return fail(NGP_EINVAL, "grid_level_scales: L too large");
+    k_level_scales<<<1, 1024, 0, as_stream(stream)>>>(out_device, L, S, H);
+    return check_launch("grid_level_scales");
+}

@@ -1,0 +1,470 @@
+// raymarch.cu — occupancy-grid ray marcher + volumetric compositor for sm_100a.
+//
+// Replaces raymarching/src/raymarching.cu: near_far_from_aabb (:91-145), sph_from_ray (:162-198),
+// morton3D / morton3D_invert (:214-254), packbits (:267-289), march_rays_train (:311-480),
+// composite_rays_train fwd/bwd (:500-682), march_rays (:700-805), composite_rays (:818-905).
+//
+// Bit-exactness contract (north_star: ray ids / sample counts bit-exact): a ray's march is a
+// sequential float recurrence, so the per-step arithmetic is kept operation-for-operation equal to
+// what nvcc emits for the reference — every multiply-add the reference's build contracts into an
+// FFMA is written here as an explicit fmaf(), divisions are IEEE, the cell index goes through the
+// same float->double->float->int chain (:374-376).  What changes is the machinery around it:
+//   * slot allocation uses one warp-aggregated atomic pair per warp (shuffle prefix scan + ballot)
+//     instead of two atomics per ray; rays of a warp therefore land in ray order (a valid instance
+//     of the reference's arbitrary atomics order),
+//   * the occupancy bitfield is read through the read-only L1 path,
+//   * compositing is unchanged per ray (sequential by definition) but loads are vectorised.
+#include "common.cuh"
+#include <float.h>
+
+namespace ngp {
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
+__device__ __forceinline__ float signf1(float x) { return copysignf(1.0f, x); }
+
+// 10-bit x 3 Morton code (bit interleave by magic multiplies)
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton_enc(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+__host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// cascade level from position / step size (raymarching.cu:42-54)
+__device__ __forceinline__ int mip_from_pos(float x, float y, float z, float max_cascade) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int e;
+    frexpf(mx, &e);
+    return (int)fminf(max_cascade - 1, fmaxf(0.f, (float)e));
+}
+__device__ __forceinline__ int mip_from_dt(float dt, float H, float max_cascade) {
+    const float mx = dt * H * 0.5f;   // reference: (dt*H) in float, *0.5 in double (exact)
+    int e;
+    frexpf(mx, &e);
+    return (int)fminf(max_cascade - 1, fmaxf(0.f, (float)e));
+}
+
+// ---- per-ray marching state -----------------------------------------------------------------
+struct RayConst {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, fH, fC, Hm1;
+    uint32_t H;
+};
+
+__device__ __forceinline__ void ray_setup(RayConst& r, const float* __restrict__ o, const float* __restrict__ d,
+                                          float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
+    r.ox = o[0]; r.oy = o[1]; r.oz = o[2];
+    r.dx = d[0]; r.dy = d[1]; r.dz = d[2];
+    r.rdx = 1.0f / r.dx; r.rdy = 1.0f / r.dy; r.rdz = 1.0f / r.dz;
+    r.bound = bound; r.dt_gamma = dt_gamma;
+    r.H = H; r.fH = (float)H; r.fC = (float)C; r.Hm1 = (float)(H - 1);
+    r.rH = 1.0f / (float)H;
+    r.H3 = (float)(H * H * H);
+    const float two_sqrt3 = 2 * 1.7320508075688772f;
+    r.dt_min = two_sqrt3 / (float)max_steps;
+    r.dt_max = two_sqrt3 * (float)(1 << (C - 1)) / (float)H;
+}
+
+// One marching decision at parameter t: returns true if the cell is occupied (a sample is taken
+// at (x,y,z) with step dt); otherwise advances t past the empty cell.  Mirrors :357-399.
+__device__ __forceinline__ bool march_probe(const RayConst& r, const uint8_t* __restrict__ grid, float& t,
+                                            float& x, float& y, float& z, float& dt) {
+    x = clampf(fmaf(t, r.dx, r.ox), -r.bound, r.bound);
+    y = clampf(fmaf(t, r.dy, r.oy), -r.bound, r.bound);
+    z = clampf(fmaf(t, r.dz, r.oz), -r.bound, r.bound);
+    dt = clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
+
+    const int level = max(mip_from_pos(x, y, z, r.fC), mip_from_dt(dt, r.fH, r.fC));
+    const float mip_bound = fminf(scalbnf(1.0f, level), r.bound);
+    const float mip_rbound = 1.0f / mip_bound;
+
+    const int nx = (int)clampf((float)(0.5 * (double)fmaf(x, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
+    const int ny = (int)clampf((float)(0.5 * (double)fmaf(y, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
+    const int nz = (int)clampf((float)(0.5 * (double)fmaf(z, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
+
+    const uint32_t index = (uint32_t)fmaf((float)level, r.H3, (float)morton_enc(nx, ny, nz));
+    const bool occ = __ldg(grid + (index >> 3)) & (1u << (index & 7u));
+    if (occ) return true;
+
+    const float tx = (fmaf(fmaf(fmaf(0.5f, signf1(r.dx), (float)nx + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -x)) * r.rdx;
+    const float ty = (fmaf(fmaf(fmaf(0.5f, signf1(r.dy), (float)ny + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -y)) * r.rdy;
+    const float tz = (fmaf(fmaf(fmaf(0.5f, signf1(r.dz), (float)nz + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -z)) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do {
+        t += clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
+    } while (t < tt);
+    return false;
+}
+
+// ---- utils ----------------------------------------------------------------------------------
+__global__ void k_near_far(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                           const float* __restrict__ aabb, uint32_t N, float min_near,
+                           float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float rdx = 1.0f / rays_d[n * 3], rdy = 1.0f / rays_d[n * 3 + 1], rdz = 1.0f / rays_d[n * 3 + 2];
+
+    float near = (aabb[0] - ox) * rdx, far = (aabb[3] - ox) * rdx;
+    if (near > far) { const float c = near; near = far; far = c; }
+    float near_y = (aabb[1] - oy) * rdy, far_y = (aabb[4] - oy) * rdy;
+    if (near_y > far_y) { const float c = near_y; near_y = far_y; far_y = c; }
+    if (near > far_y || near_y > far) { nears[n] = fars[n] = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = (aabb[2] - oz) * rdz, far_z = (aabb[5] - oz) * rdz;
+    if (near_z > far_z) { const float c = near_z; near_z = far_z; far_z = c; }
+    if (near > far_z || near_z > far) { nears[n] = fars[n] = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+__global__ void k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                               uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ox * dx + oy * dy + oz * dz;
+    const float Cc = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bh + sqrtf(Bh * Bh - A * Cc)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    const float rpi = 0.3183098861837907f;
+    coords[n * 2] = 2 * theta * rpi - 1;
+    coords[n * 2 + 1] = phi * rpi;
+}
+
+__global__ void k_morton3D(const int* __restrict__ coords, uint32_t N, int* __restrict__ indices) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    indices[n] = (int)morton_enc(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+
+__global__ void k_morton3D_invert(const int* __restrict__ indices, uint32_t N, int* __restrict__ coords) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const int ind = indices[n];
+    coords[n * 3] = (int)compact3((uint32_t)(ind >> 0));
+    coords[n * 3 + 1] = (int)compact3((uint32_t)(ind >> 1));
+    coords[n * 3 + 2] = (int)compact3((uint32_t)(ind >> 2));
+}
+
+// 8 floats -> 1 occupancy byte; two 128-bit loads per thread
+__global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* __restrict__ bitfield) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(grid) + (size_t)n * 2);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(grid) + (size_t)n * 2 + 1);
+    uint32_t bits = 0;
+    bits |= (a.x > thresh) ? 1u : 0u;   bits |= (a.y > thresh) ? 2u : 0u;
+    bits |= (a.z > thresh) ? 4u : 0u;   bits |= (a.w > thresh) ? 8u : 0u;
+    bits |= (b.x > thresh) ? 16u : 0u;  bits |= (b.y > thresh) ? 32u : 0u;
+    bits |= (b.z > thresh) ? 64u : 0u;  bits |= (b.w > thresh) ? 128u : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// ---- training marcher ------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                   const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                   uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
+                   const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+                   float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
+                   const float* __restrict__ noises) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const bool active = n < N;
+    const uint32_t lane = threadIdx.x & 31u;
+
+    RayConst r;
+    float far = 0.f, t0 = 0.f;
+    uint32_t num_steps = 0;
+    if (active) {
+        ray_setup(r, rays_o + (size_t)n * 3, rays_d + (size_t)n * 3, bound, dt_gamma, max_steps, C, H);
+        const float near = nears[n];
+        far = fars[n];
+        t0 = fmaf(clampf(near * dt_gamma, r.dt_min, r.dt_max), noises[n], near);
+        // pass 1: count occupied steps
+        float t = t0, x, y, z, dt;
+        while (t < far && num_steps < max_steps) {
+            if (march_probe(r, grid, t, x, y, z, dt)) { num_steps++; t += dt; }
+        }
+    }
+
+    // warp-aggregated slot reservation: inclusive scan of num_steps, ballot-rank of active lanes,
+    // one atomic pair by the last active lane's warp leader.
+    uint32_t incl = num_steps;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+    uint32_t base_pt = 0, base_ray = 0;
+    if (lane == 0) {
+        base_pt = (uint32_t)atomicAdd(counter, (int)warp_total);
+        base_ray = (uint32_t)atomicAdd(counter + 1, (int)__popc(act_mask));
+    }
+    base_pt = __shfl_sync(0xffffffffu, base_pt, 0);
+    base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
+    if (!active) return;
+
+    const uint32_t point_index = base_pt + incl - num_steps;
+    const uint32_t ray_index = base_ray + __popc(act_mask & ((1u << lane) - 1u));
+    rays[ray_index * 3] = (int)n;
+    rays[ray_index * 3 + 1] = (int)point_index;
+    rays[ray_index * 3 + 2] = (int)num_steps;
+
+    if (num_steps == 0) return;
+    if (point_index + num_steps > M) return;
+
+    // pass 2: re-march and emit samples
+    float* __restrict__ px = xyzs + (size_t)point_index * 3;
+    float* __restrict__ pd = dirs + (size_t)point_index * 3;
+    float* __restrict__ pl = deltas + (size_t)point_index * 2;
+    float t = t0, last_t = t0, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < num_steps) {
+        if (march_probe(r, grid, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            *reinterpret_cast<float2*>(pl) = make_float2(dt, t - last_t);
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            step++;
+        }
+    }
+}
+
+// ---- training compositor ---------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                      const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M, uint32_t N,
+                      float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth,
+                      float* __restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) {
+        weights_sum[index] = 0; depth[index] = 0;
+        image[index * 3] = 0; image[index * 3 + 1] = 0; image[index * 3 + 2] = 0;
+        return;
+    }
+    const float* __restrict__ sg = sigmas + offset;
+    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
+    for (uint32_t step = 0; step < num_steps; ++step) {
+        const float2 dd = __ldg(dl + step);
+        const float alpha = 1.0f - __expf(-__ldg(sg + step) * dd.x);
+        const float weight = alpha * T;
+        r = fmaf(weight, __ldg(cl + step * 3), r);
+        g = fmaf(weight, __ldg(cl + step * 3 + 1), g);
+        b = fmaf(weight, __ldg(cl + step * 3 + 2), b);
+        t += dd.y;
+        d = fmaf(weight, t, d);
+        ws += weight;
+        T *= 1.0f - alpha;
+        if (T < T_thresh) break;
+    }
+    weights_sum[index] = ws; depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
+                      const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                      const float* __restrict__ deltas, const int* __restrict__ rays,
+                      const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M,
+                      uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
+    if (num_steps == 0 || offset + num_steps > M) return;
+    const float gws = grad_weights_sum[index];
+    const float gr = grad_image[index * 3], gg = grad_image[index * 3 + 1], gb = grad_image[index * 3 + 2];
+    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
+    const float ws_final = weights_sum[index];
+    const float* __restrict__ sg = sigmas + offset;
+    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+    float* __restrict__ gs = grad_sigmas + offset;
+    float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
+    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
+    for (uint32_t step = 0; step < num_steps; ++step) {
+        const float d0 = __ldg(dl + step).x;
+        const float c0 = __ldg(cl + step * 3), c1 = __ldg(cl + step * 3 + 1), c2 = __ldg(cl + step * 3 + 2);
+        const float alpha = 1.0f - __expf(-__ldg(sg + step) * d0);
+        const float weight = alpha * T;
+        r = fmaf(weight, c0, r);
+        g = fmaf(weight, c1, g);
+        b = fmaf(weight, c2, b);
+        ws += weight;
+        T *= 1.0f - alpha;
+        gc[step * 3] = gr * weight;
+        gc[step * 3 + 1] = gg * weight;
+        gc[step * 3 + 2] = gb * weight;
+        gs[step] = d0 * (gr * (T * c0 - (r_final - r)) + gg * (T * c1 - (g_final - g)) +
+                         gb * (T * c2 - (b_final - b)) + gws * (1 - ws_final));
+        if (T < T_thresh) break;
+    }
+}
+
+// ---- inference -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+             const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, float dt_gamma,
+             uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+             const float* __restrict__ nears, const float* __restrict__ fars, float* __restrict__ xyzs,
+             float* __restrict__ dirs, float* __restrict__ deltas, const float* __restrict__ noises) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    RayConst r;
+    ray_setup(r, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, bound, dt_gamma, max_steps, C, H);
+    float* __restrict__ px = xyzs + (size_t)n * n_step * 3;
+    float* __restrict__ pd = dirs + (size_t)n * n_step * 3;
+    float* __restrict__ pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const float far = fars[index];
+    (void)nears;
+    t = fmaf(clampf(t * dt_gamma, r.dt_min, r.dt_max), noises[n], t);
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (march_probe(r, grid, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            pl[0] = dt; pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            step++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restrict__ rays_alive,
+                 float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                 const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth,
+                 float* __restrict__ image) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float* __restrict__ sg = sigmas + (size_t)n * n_step;
+    const float* __restrict__ cl = rgbs + (size_t)n * n_step * 3;
+    const float* __restrict__ dl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float d0 = dl[step * 2];
+        if (d0 == 0) break;
+        const float alpha = 1.0f - __expf(-sg[step] * d0);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += dl[step * 2 + 1];
+        d = fmaf(weight, t, d);
+        r = fmaf(weight, cl[step * 3], r);
+        g = fmaf(weight, cl[step * 3 + 1], g);
+        b = fmaf(weight, cl[step * 3 + 2], b);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else rays_t[index] = t;
+    weights_sum[index] = weight_sum;
+    depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+}  // namespace ngp
+
+using namespace ngp;
+
+#define NGP_LAUNCH_1D(KERNEL, COUNT, TPB, NAME, ...)                                   \
+    do {                                                                               \
+        if ((COUNT) == 0) return NGP_OK;                                               \
+        KERNEL<<<div_up((uint32_t)(COUNT), (uint32_t)(TPB)), (TPB), 0, as_stream(stream)>>>(__VA_ARGS__); \
+        return check_launch(NAME);                                                     \
+    } while (0)
+
+extern "C" int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                      float min_near, float* nears, float* fars, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_near_far, N, 128, "near_far_from_aabb", rays_o, rays_d, aabb, N, min_near, nears, fars);
+}
+extern "C" int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                                ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_sph_from_ray, N, 128, "sph_from_ray", rays_o, rays_d, radius, N, coords);
+}
+extern "C" int ngp_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_morton3D, N, 256, "morton3D", coords, N, indices);
+}
+extern "C" int ngp_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_morton3D_invert, N, 256, "morton3D_invert", indices, N, coords);
+}
+extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield,
+                            ngp_stream_t stream) {
+    if ((reinterpret_cast<uintptr_t>(grid) & 15) != 0) return fail(NGP_EINVAL, "packbits: grid must be 16-byte aligned");
+    NGP_LAUNCH_1D(k_packbits, N, 256, "packbits", grid, N, density_thresh, bitfield);
+}
+extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                    float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                    uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                                    float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                    ngp_stream_t stream) {
+    if (C < 1 || C > 24) return fail(NGP_EINVAL, "march_rays_train: cascade count out of range");
+    NGP_LAUNCH_1D(k_march_rays_train, N, 128, "march_rays_train", rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
+                  C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises);
+}
+extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                                const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                                float* weights_sum, float* depth, float* image,
+                                                ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_composite_train_fwd, N, 128, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
+                  T_thresh, weights_sum, depth, image);
+}
+extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                 const float* sigmas, const float* rgbs, const float* deltas,
+                                                 const int32_t* rays, const float* weights_sum, const float* image,
+                                                 uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                                 float* grad_rgbs, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_composite_train_bwd, N, 128, "composite_rays_train_backward", grad_weights_sum, grad_image, sigmas,
+                  rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+}
+extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                              const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                              const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                              ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_march_rays, n_alive, 128, "march_rays", n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
+                  dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs, deltas, noises);
+}
+extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive,
+                                  float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
+                                  float* weights_sum, float* depth, float* image, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_composite_rays, n_alive, 128, "composite_rays", n_alive, n_step, T_thresh, rays_alive, rays_t,
+                  sigmas, rgbs, deltas, weights_sum, depth, image);
+}

@@ -1,0 +1,127 @@
+"""nerf_step.py — the caller side of the hot path, restated for measurement and tests.
+
+The reference's callers (nerf/network_ff.py NeRFNetwork.forward/density :51-89 and the training branch of
+nerf/renderer.py run_cuda :280-321) live in /root/reference and cannot travel to the GPU box, so this
+module re-expresses exactly that call sequence on top of the drop-in packages
+(gridencoder.GridEncoder -> ffmlp.FFMLP -> trunc_exp; shencoder.SHEncoder (+) geo_feat (+) pad ->
+ffmlp.FFMLP -> sigmoid; raymarching.near_far_from_aabb / march_rays_train / composite_rays_train).
+It is host glue, not a kernel; bench.py drives it, tests check it against the oracle.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from gridencoder import GridEncoder
+from shencoder import SHEncoder
+from ffmlp import FFMLP
+import raymarching
+
+
+class _trunc_exp(torch.autograd.Function):
+    """activation.py:5-18 of the reference."""
+    @staticmethod
+    @torch.amp.custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type='cuda')
+    def backward(ctx, g):
+        x = ctx.saved_tensors[0]
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+trunc_exp = _trunc_exp.apply
+
+
+class NeRFFieldFF(nn.Module):
+    """Field of nerf/network_ff.py:11-89 (hashgrid 16x2 -> FFMLP 32-64-64-16; SH4 (+) 15 geo (+) pad -> FFMLP 32-64-64-64-16)."""
+
+    def __init__(self, bound=1, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
+                 density_scale=1, min_near=0.2, density_thresh=0.01, grid_size=128):
+        super().__init__()
+        self.bound = bound
+        self.cascade = 1 + math.ceil(math.log2(bound))
+        self.grid_size = grid_size
+        self.density_scale = density_scale
+        self.min_near = min_near
+        self.density_thresh = density_thresh
+        self.geo_feat_dim = geo_feat_dim
+        self.encoder = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                                   desired_resolution=2048 * bound, gridtype='hash', align_corners=False)
+        self.sigma_net = FFMLP(input_dim=self.encoder.output_dim, output_dim=1 + geo_feat_dim, hidden_dim=hidden_dim,
+                               num_layers=num_layers)
+        self.encoder_dir = SHEncoder(input_dim=3, degree=4)
+        self.color_net = FFMLP(input_dim=self.encoder_dir.output_dim + geo_feat_dim + 1, output_dim=3,
+                               hidden_dim=hidden_dim_color, num_layers=num_layers_color)
+        aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
+        self.register_buffer('aabb_train', aabb)
+        self.register_buffer('density_bitfield', torch.zeros(self.cascade * grid_size ** 3 // 8, dtype=torch.uint8))
+        self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
+        self.mean_count = 0
+        self.local_step = 0
+
+    def forward(self, x, d):
+        x = self.encoder(x, bound=self.bound)
+        h = self.sigma_net(x)
+        sigma = trunc_exp(h[..., 0])
+        geo_feat = h[..., 1:]
+        d = self.encoder_dir(d)
+        p = torch.zeros_like(geo_feat[..., :1])
+        h = torch.cat([d, geo_feat, p], dim=-1)
+        h = self.color_net(h)
+        rgb = torch.sigmoid(h)
+        return sigma, rgb
+
+    def density(self, x):
+        x = self.encoder(x, bound=self.bound)
+        h = self.sigma_net(x)
+        return {'sigma': trunc_exp(h[..., 0]), 'geo_feat': h[..., 1:]}
+
+    def render_train(self, rays_o, rays_d, bg_color=1, perturb=True, force_all_rays=False, dt_gamma=0, max_steps=1024,
+                     T_thresh=1e-4):
+        """training branch of renderer.py run_cuda (:256-321)."""
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train, self.min_near)
+        counter = self.step_counter[self.local_step % 16]
+        counter.zero_()
+        self.local_step += 1
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield,
+                                                                self.cascade, self.grid_size, nears, fars, counter,
+                                                                self.mean_count, perturb, 128, force_all_rays, dt_gamma,
+                                                                max_steps)
+        sigmas, rgbs = self(xyzs, dirs)
+        sigmas = self.density_scale * sigmas
+        weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {'image': image, 'depth': depth, 'weights_sum': weights_sum, 'n_samples': xyzs.shape[0]}
+
+    def update_mean_count(self):
+        """tail of renderer.py update_extra_state (:532-536)."""
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+        self.local_step = 0
+
+
+def train_step(model, rays_o, rays_d, target, optimizer=None, scaler=None, **render_kw):
+    """One reference training iteration (nerf/utils.py:861-868): autocast forward, MSE, scaled backward, optimizer."""
+    if optimizer is not None:
+        optimizer.zero_grad(set_to_none=True)
+    with torch.autocast('cuda', dtype=torch.float16):
+        out = model.render_train(rays_o, rays_d, **render_kw)
+        loss = torch.nn.functional.mse_loss(out['image'], target)
+    if scaler is not None:
+        scaler.scale(loss).backward()
+        if optimizer is not None:
+            scaler.step(optimizer)
+            scaler.update()
+    else:
+        loss.backward()
+        if optimizer is not None:
+            optimizer.step()
+    return loss.detach(), out
