@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — training rays/sec of the fused NeRF hot path on synthetic 800x800 rays (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W        # CPU arm (pure-PyTorch fp32 path, oracle/torch_ref.py)
+
+One "step" = one optimisation step over `--rays-per-step` rays (default: a full 800x800 frame = 640 000 rays) of a
+synthetic blender-format scene: near/far -> occupancy-grid march (steady-state mean_count path) -> hash-grid encode ->
+sigma MLP -> SH -> color MLP -> composite -> MSE -> backward (-> gradient allreduce at N>1) -> GradScaler + Adam.
+Prints ONE JSON line (rank 0).  `value` = device-timed whole-job rays/s with inputs resident in HBM; `e2e` = the same
+through the public API with per-step pinned-host -> device copies of the rays/targets and a device -> host read of
+the loss inside the timed region.  Strong scaling: the step's rays are split across ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "torch-ngp_b200")]
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+H_IMG = W_IMG = 800
+METRIC = "training rays/sec (device-timed) at 800x800, L=16 hashgrid"
+UNIT = "rays/s"
+N_CAMERAS = 4          # distinct full frames cycled through (inputs >> L2: ~3-8 GB of activations per step)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays-per-step", type=int, default=H_IMG * W_IMG)
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(rows)}
+
+
+def units_of(name, args):
+    """(samples_or_rays, algorithmic bytes, flops) of one C-ABI call — SURVEY §8(d) per-unit figures."""
+    if name == "ngp_grid_encode_forward":
+        B, D, C, L, dtype = args[4], args[5], args[6], args[7], args[14]
+        sz = 2 if dtype == 1 else 4
+        return B, B * (4 * D + L * (1 << D) * C * sz + L * C * sz), 0
+    if name == "ngp_grid_encode_backward":
+        B, D, C, L, dtype = args[5], args[6], args[7], args[8], args[16]
+        sz = 2 if dtype == 1 else 4
+        return B, B * (4 * D + L * C * sz + L * (1 << D) * C * sz), 0
+    if name in ("ngp_ffmlp_forward", "ngp_ffmlp_inference"):
+        B, ind, outd, hid, nl = args[2], args[3], args[4], args[5], args[6]
+        params = hid * (ind + hid * (nl - 1) + outd)
+        return B, B * 2 * (ind + outd + (nl * hid if name == "ngp_ffmlp_forward" else 0)), 2 * params * B
+    if name == "ngp_ffmlp_backward":
+        B, ind, outd, hid, nl = args[4], args[5], args[6], args[7], args[8]
+        params = hid * (ind + hid * (nl - 1) + outd)
+        return B, B * 2 * (outd + ind + 3 * nl * hid + ind), 4 * params * B
+    if name == "ngp_march_rays_train":
+        return args[6], None, 0      # bytes depend on the emitted sample count (filled in by the caller)
+    if name == "ngp_composite_rays_train_forward":
+        M, N = args[4], args[5]
+        return N, 24 * M + 32 * N, 0
+    if name == "ngp_composite_rays_train_backward":
+        M, N = args[8], args[9]
+        return N, 40 * M + 44 * N, 0
+    if name == "ngp_sh_encode_forward":
+        B, deg = args[2], args[4]
+        return B, B * (12 + 4 * deg * deg), 0
+    if name == "ngp_near_far_from_aabb":
+        return args[3], args[3] * 32, 0
+    return 0, 0, 0
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_arm(args, rays_per_step, steps, warmup):
+    from oracle import torch_ref as T
+    import ngp_synth as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    poses = S.make_cameras(N_CAMERAS, seed=11)
+    g = torch.Generator().manual_seed(3)
+    n_pool = max(rays_per_step * 4, 2048)
+    inds = torch.randint(0, H_IMG * W_IMG, (n_pool,), generator=g)
+    ro, rd = S.get_rays(poses[0], S.intrinsics(H_IMG, W_IMG), H_IMG, W_IMG, inds)
+    target = torch.rand(n_pool, 3, generator=g)
+    sec, loss = T.train_steps(rays_per_step, steps, warmup, ro, rd, target, threads=cores)
+    return dict(value=rays_per_step / sec, unit=UNIT, cores=cores, kind="port",
+                sample=f"{steps} steps x {rays_per_step} random rays of the 800x800 frame, 512 samples/ray (reference `run` path), "
+                       f"fp32 torch on {cores} host threads; {sec * 1e3:.1f} ms/step"), sec
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def build_model(dev):
+    import ngp_synth as S
+    from nerf_step import NeRFFieldFF
+    torch.manual_seed(1)
+    model = NeRFFieldFF(bound=1).to(dev).train()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        model.encoder.embeddings.copy_((torch.rand(model.encoder.embeddings.shape, generator=g) * 2 - 1) * 1e-4)
+    grid, fill = S.box_union_density(128, seed=12)
+    model.density_bitfield.copy_(torch.from_numpy(S.packbits_np(grid.numpy())).to(dev))
+    return model, fill
+
+
+def make_inputs(rays_total, lo, hi, dev):
+    """Per-camera (rays_o, rays_d, target) for this rank's ray range, pinned on the host and resident on the device."""
+    import ngp_synth as S
+    poses = S.make_cameras(N_CAMERAS, seed=11)
+    intr = S.intrinsics(H_IMG, W_IMG)
+    host, devs = [], []
+    for c in range(N_CAMERAS):
+        g = torch.Generator().manual_seed(100 + c)
+        if rays_total == H_IMG * W_IMG:
+            inds = torch.arange(H_IMG * W_IMG)
+        else:
+            inds = torch.randint(0, H_IMG * W_IMG, (rays_total,), generator=g)
+        ro, rd = S.get_rays(poses[c], intr, H_IMG, W_IMG, inds[lo:hi])
+        tgt = torch.rand(rays_total, 3, generator=g)[lo:hi].contiguous()
+        h = tuple(t.contiguous().pin_memory() for t in (ro, rd, tgt))
+        host.append(h)
+        devs.append(tuple(t.to(dev) for t in h))
+    return host, devs
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        # CPU arm: rank 0 alone runs; other ranks exit 0 without work
+        if rank != 0:
+            return
+        cb, sec = cpu_arm(args, args.cpu_rays, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "nerf_train_800x800_synthetic_lego_boxes", "rays_per_step": args.cpu_rays,
+                           "note": "reference pure-PyTorch path (--fp32, no --cuda_ray) restated for CPU; bounded sample of the GPU arm's workload"},
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: CUDA device required (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import _ngp_b200 as nb
+    import ngp_dp
+    from nerf_step import train_step
+    nb.load()
+
+    R = args.rays_per_step
+    lo, hi = ngp_dp.shard_range(R, rank, world)
+    model, fill = build_model(dev)
+    if world > 1:
+        ngp_dp.broadcast_module(model)
+    host_in, dev_in = make_inputs(R, lo, hi, dev)
+    params = [model.encoder.embeddings, model.sigma_net.weights, model.color_net.weights]
+    bucket = ngp_dp.FlatGradBucket(params)
+    opt = torch.optim.Adam(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, fused=True)
+    scaler = torch.amp.GradScaler("cuda", init_scale=128.0)
+    stage = [tuple(torch.empty_like(t) for t in dev_in[0])]   # device staging for the e2e H2D copies
+
+    def step(ro, rd, tgt):
+        bucket.zero()
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.render_train(ro, rd, perturb=True)
+            # sum over local rays / global ray count: averaging the allreduce over ranks is then not needed
+            loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)
+        scaler.scale(loss).backward()
+        if world > 1:
+            bucket.allreduce(average=False)
+        scaler.step(opt)
+        scaler.update()
+        return loss, out
+
+    # ---- establish the steady-state sample budget (reference: mean_count after the first epoch) ----
+    counts = []
+    for c in range(N_CAMERAS):
+        model.mean_count = 0
+        loss, out = step(*dev_in[c])
+        counts.append(int(model.step_counter[(model.local_step - 1) % 16, 0].item()))
+    model.mean_count = max(counts)       # no ray is dropped in the timed region (dropping = skipped work)
+    samples_per_step_local = float(np.mean(counts))
+
+    def run_loop(n, e2e):
+        last = None
+        for i in range(n):
+            c = i % N_CAMERAS
+            if e2e:
+                for dst, src in zip(stage[0], host_in[c]):
+                    dst.copy_(src, non_blocking=True)
+                loss, _ = step(*stage[0])
+                last = loss.item()            # device -> host read of the step's result
+            else:
+                loss, _ = step(*dev_in[c])
+        return last
+
+    def timed(n, e2e, profile=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        if profile:
+            nb.profile_begin()
+        nb.reset_launch_count()
+        e0.record()
+        run_loop(n, e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = nb.launch_count()
+        rec = nb.profile_end() if profile else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches, rec
+
+    W = max(args.warmup, 3)
+    run_loop(W, False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    t0 = sampler.mark()
+    ms_total, launches, rec = timed(args.steps, False, profile=True)
+    t1 = sampler.mark()
+    clocks = sampler.stop(t0, t1)
+    run_loop(2, True)
+    ms_e2e, _, _ = timed(args.steps, True)
+
+    value = R * args.steps / (ms_total * 1e-3)
+    e2e_value = R * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host_in[0])
+
+    # ---- per-entry-point device time inside the timed region -> dominant kernel + roofline ----
+    agg = {}
+    for name, a, s0, s1 in rec:
+        n, by, fl = units_of(name, a)
+        d = agg.setdefault(name, dict(ms=0.0, calls=0, bytes=0, flops=0, units=0))
+        d["ms"] += s0.elapsed_time(s1); d["calls"] += 1; d["units"] += n
+        if name == "ngp_march_rays_train":
+            by = int(32 * samples_per_step_local + 48 * n)
+        d["bytes"] += by or 0; d["flops"] += fl
+    pk = peaks()
+    kern_ms = sum(d["ms"] for d in agg.values())
+    dom = max(agg, key=lambda k: agg[k]["ms"])
+    dd = agg[dom]
+    per_launch_ms = dd["ms"] / dd["calls"]
+    if dom.startswith("ngp_ffmlp"):
+        ach = dd["flops"] / dd["calls"] / (per_launch_ms * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"]}
+    else:
+        ach = dd["bytes"] / dd["calls"] / (per_launch_ms * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+    roof.update({"traffic": None, "peak_source": pk["src"], "avg_launch_ms": per_launch_ms,
+                 "share_of_step": dd["ms"] / ms_total, "algorithmic_bytes_per_launch": dd["bytes"] / dd["calls"]})
+    breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
+                     "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None,
+                     "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "nerf_train_800x800_synthetic_lego_boxes", "rays_per_step": R, "rays_per_rank": hi - lo,
+                       "samples_per_ray_mean": samples_per_step_local / max(1, hi - lo), "occupancy_fill": fill,
+                       "hashgrid": "L=16 F=2 T=2^19 base16 ->2048", "mlp": "FFMLP 32-64-64-16 + 32-64-64-64-16 fp16/fp32-acc",
+                       "optimizer": "GradScaler + fused Adam (in timed region)", "parallelism": f"dp{world} (rays sharded, 1 allreduce/step)",
+                       "l2": "inputs_exceed_l2 (per-step activations of several GB; 4 camera frames cycled)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world > 1 else h2d, "d2h_bytes_per_step": 4 * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "kernel_time_share": kern_ms / ms_total, "kernels": breakdown}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb, _ = cpu_arm(args, args.cpu_rays, 3, 1)
+            line["cpu_baseline"] = cb
+        except Exception as e:   # the baseline is a reported number, never a reason to lose the bench line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        try:
+            import bench_ref_cuda
+            line["ref_cuda"] = bench_ref_cuda.measure(dev, R, dev_in, model, steps=max(3, min(args.steps, 10)))
+        except Exception as e:
+            line["ref_cuda"] = {"unavailable": str(e)[:200]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

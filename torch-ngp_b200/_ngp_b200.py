@@ -80,10 +80,31 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profile = None   # when a list: (name, args, start_event, end_event) per call (bench.py roofline timing)
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    global _profile
+    rec, _profile = _profile, None
+    return rec
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on the current stream; raise RuntimeError on a non-zero code."""
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if _profile is not None:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        _profile.append((name, args, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.ngp_last_error().decode()}")
 
