@@ -127,3 +127,32 @@ def measure(dev, R_rays, dev_in, model, steps=5, warmup=2):
     ms = e0.elapsed_time(e1) / steps
     return {"value": R_rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps, "loss": float(loss),
             "what": "unmodified reference CUDA extensions (gridencoder, ffmlp+CUTLASS 2.8, shencoder, raymarching) built for sm_100, same step, same GPU"}
+
+
+if __name__ == "__main__":
+    import argparse, json, os, sys
+    ROOT = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "torch-ngp_b200")]
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rays-per-step", type=int, default=640000)
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    import bench
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    model, _ = bench.build_model(dev)
+    _, dev_in = bench.make_inputs(a.rays_per_step, 0, a.rays_per_step, dev)
+    # steady-state sample budget, measured with the reference marcher itself
+    nears, fars = R.near_far_from_aabb(dev_in[0][0], dev_in[0][1], model.aabb_train, model.min_near)
+    counts = []
+    for ro, rd, _t in dev_in:
+        n_, f_ = R.near_far_from_aabb(ro, rd, model.aabb_train, model.min_near)
+        c = torch.zeros(2, dtype=torch.int32, device=dev)
+        mod = R.mod("raymarching")
+        N = ro.shape[0]
+        e = torch.empty(0, 3, device=dev); e2 = torch.empty(0, 2, device=dev)
+        mod.march_rays_train(ro, rd, model.density_bitfield, 1.0, 0.0, 1024, N, 1, 128, 0, n_, f_, e, e, e2,
+                             torch.empty(N, 3, dtype=torch.int32, device=dev), c, torch.ones(N, device=dev))
+        counts.append(int(c[0].item()))
+    model.mean_count = max(counts)
+    print(json.dumps(measure(dev, a.rays_per_step, dev_in, model, steps=a.steps)))

@@ -142,4 +142,4 @@ def train_steps(n_rays, steps, warmup, rays_o, rays_d, target, threads=None, see
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return float(np.mean(times)), float(loss)
+    return float(np.mean(times)), float(loss.detach())

