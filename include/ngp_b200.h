@@ -95,7 +95,7 @@ int ngp_ffmlp_inference(const void* inputs, const void* weights, uint32_t B, uin
                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
                         uint32_t activation, uint32_t output_activation, void* inference_buffer,
                         void* outputs, ngp_stream_t stream);
-/* grad [B,output_dim]; backward_buffer [num_layers,B,hidden] scratch (written: dL/d pre-activation,
+/* grad [B,output_dim]; backward_buffer [num_layers,B,hidden] scratch, NULLABLE when num_layers <= 5 (written: dL/d pre-activation,
  * deepest layer first, as ffmlp.cu:749-895); grad_inputs [B,input_dim] iff calc_grad_inputs;
  * grad_weights same layout as weights (fp16, overwritten).  workspace: at least
  * ngp_ffmlp_backward_workspace_bytes() bytes of device scratch (fp32 partial weight grads). */

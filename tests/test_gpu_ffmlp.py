@@ -106,6 +106,33 @@ def test_backward_vs_oracle(cfg):
     assert rel_err(ws.cpu().numpy(), gw_ref) < 1e-3
 
 
+@pytest.mark.parametrize("cfg", [dict(input_dim=32, num_layers=2), dict(input_dim=32, num_layers=3), dict(input_dim=32, num_layers=6)])
+def test_backward_variants(cfg):
+    """no grad_inputs / NULL backward_buffer (fused kernel) and the deep-net two-kernel fallback (num_layers=6 -> 7 matmuls);
+    many tiles per CTA so the persistent accumulate path is exercised."""
+    from oracle import oracle as O
+    import _ngp_b200 as nb
+    B = 128 * 1500
+    x, w = _mk(B, **cfg)
+    nl, ind = cfg["num_layers"], cfg["input_dim"]
+    xd, wd = x.cuda(), w.cuda()
+    fb = torch.empty(nl, B, 64, dtype=torch.half, device="cuda"); y = torch.empty(B, 16, dtype=torch.half, device="cuda")
+    nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), B, ind, 16, 64, nl, 0, 6, fb.data_ptr(), y.data_ptr())
+    g = (torch.randn(B, 16, generator=gen(5)) * 0.1).half()
+    gi_ref, gw_ref, bb_ref = O.mlp_backward(g.numpy(), x.numpy(), w.numpy(), fb.cpu().numpy(), ind, 64, nl)
+    gd = g.cuda()
+    nbytes = nb.load().ngp_ffmlp_backward_workspace_bytes(B, ind, 16, 64, nl)
+    ws = torch.empty(nbytes // 4, device="cuda"); gw = torch.zeros_like(wd)
+    bb = torch.zeros(nl, B, 64, dtype=torch.half, device="cuda") if nl + 1 > 6 else None
+    for calc_gi in (0, 1):
+        gi = torch.zeros(B, ind, dtype=torch.half, device="cuda")
+        nb.call("ngp_ffmlp_backward", gd.data_ptr(), xd.data_ptr(), wd.data_ptr(), fb.data_ptr(), B, ind, 16, 64, nl, 0, 6, calc_gi,
+                nb.ptr(bb), gi.data_ptr() if calc_gi else None, gw.data_ptr(), ws.data_ptr(), nbytes)
+        assert rel_err(ws.cpu().numpy(), gw_ref) < 2e-3
+        if calc_gi:
+            assert rel_err(gi.cpu().numpy(), gi_ref) < 2e-3
+
+
 def test_module_autograd_matches_torch_mlp():
     """FFMLP module (pad-128 rule, autocast, seed-42 init) vs the reference's own nn.Linear restatement
     (testing/test_ffmlp.py:11-43) in fp32: 1e-3 of the output scale (north_star tolerance)."""

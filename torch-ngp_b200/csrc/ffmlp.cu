@@ -39,29 +39,29 @@ static constexpr float K_ACT = 10.0f;         // reference utils.h: squareplus /
 
 enum Act : uint32_t { ACT_RELU = 0, ACT_EXP = 1, ACT_SINE = 2, ACT_SIGMOID = 3, ACT_SQUAREPLUS = 4, ACT_SOFTPLUS = 5, ACT_NONE = 6 };
 
-__device__ __forceinline__ float act_fwd(uint32_t a, float x) {
-    switch (a) {
-        case ACT_RELU: return x > 0.f ? x : 0.f;
-        case ACT_EXP: return expf(x);
-        case ACT_SINE: return sinf(x);
-        case ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
-        case ACT_SQUAREPLUS: { const float t = x * K_ACT; return 0.5f * (t + sqrtf(t * t + 4)) / K_ACT; }
-        case ACT_SOFTPLUS: return logf(expf(x * K_ACT) + 1.0f) / K_ACT;
-        default: return x;
-    }
+// Activations are compile-time template parameters: a runtime switch inlined 64x per thread per layer
+// blew the kernel up to ~570 KB of SASS and made it instruction-fetch bound (ncu r1: 65% of stall samples
+// "no_instructions", tensor pipe 0.9%).
+template <uint32_t A>
+__device__ __forceinline__ float act_fwd(float x) {
+    if constexpr (A == ACT_RELU) return fmaxf(x, 0.f);
+    else if constexpr (A == ACT_EXP) return expf(x);
+    else if constexpr (A == ACT_SINE) return sinf(x);
+    else if constexpr (A == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
+    else if constexpr (A == ACT_SQUAREPLUS) { const float t = x * K_ACT; return 0.5f * (t + sqrtf(t * t + 4)) / K_ACT; }
+    else if constexpr (A == ACT_SOFTPLUS) return logf(expf(x * K_ACT) + 1.0f) / K_ACT;
+    else return x;
 }
 // dL/dpre = g * act'(.) expressed through the stored post-activation value f (reference
 // utils.h warp_activation_backward)
-__device__ __forceinline__ float act_bwd(uint32_t a, float g, float f) {
-    switch (a) {
-        case ACT_RELU: return f > 0.f ? g : 0.f;
-        case ACT_EXP: return g * f;
-        case ACT_SINE: return g;   // reference: unsupported (needs pre-activations), leaves grad unchanged
-        case ACT_SIGMOID: return g * (f * (1.0f - f));
-        case ACT_SQUAREPLUS: { const float y = f * K_ACT; return g * (y * y / (y * y + 1)); }
-        case ACT_SOFTPLUS: return g * (1.0f - expf(-f * K_ACT));
-        default: return g;
-    }
+template <uint32_t A>
+__device__ __forceinline__ float act_bwd(float g, float f) {
+    if constexpr (A == ACT_RELU) return f > 0.f ? g : 0.f;
+    else if constexpr (A == ACT_EXP) return g * f;
+    else if constexpr (A == ACT_SIGMOID) return g * (f * (1.0f - f));
+    else if constexpr (A == ACT_SQUAREPLUS) { const float y = f * K_ACT; return g * (y * y / (y * y + 1)); }
+    else if constexpr (A == ACT_SOFTPLUS) return g * (1.0f - expf(-f * K_ACT));
+    else return g;   // None; Sine: the reference leaves the gradient unchanged (needs pre-activations)
 }
 
 __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
@@ -111,11 +111,11 @@ __device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_addr, ui
 }
 
 // ================================ forward / inference ==========================================
-template <bool TRAIN>
+template <bool TRAIN, uint32_t ACT>
 __global__ void __launch_bounds__(128)
 k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ weights,
                 __half* __restrict__ forward_buffer, __half* __restrict__ outputs, const uint32_t B,
-                const uint32_t in_dim, const uint32_t num_layers, const uint32_t activation) {
+                const uint32_t in_dim, const uint32_t num_layers) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -185,8 +185,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
                     uint32_t p[16];
 #pragma unroll
                     for (uint32_t i = 0; i < 16; ++i)
-                        p[i] = pack_h2(act_fwd(activation, __uint_as_float(v[2 * i])),
-                                       act_fwd(activation, __uint_as_float(v[2 * i + 1])));
+                        p[i] = pack_h2(act_fwd<ACT>(__uint_as_float(v[2 * i])), act_fwd<ACT>(__uint_as_float(v[2 * i + 1])));
 #pragma unroll
                     for (uint32_t c = 0; c < 4; ++c) {
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
@@ -220,11 +219,12 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
 // ================================ backward: activation gradients ===============================
 // grad [B,16]; forward_buffer [num_layers,B,64]; backward_buffer [num_layers,B,64];
 // grad_inputs [B,in_dim] or null.
+template <uint32_t ACT>
 __global__ void __launch_bounds__(128)
 k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ weights,
                  const __half* __restrict__ forward_buffer, __half* __restrict__ backward_buffer,
                  __half* __restrict__ grad_inputs, const uint32_t B, const uint32_t in_dim,
-                 const uint32_t num_layers, const uint32_t activation) {
+                 const uint32_t num_layers) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -304,8 +304,7 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
 #pragma unroll
                     for (uint32_t i = 0; i < 16; ++i) {
                         const float2 ff = __half22float2(fh[i]);
-                        p[i] = pack_h2(act_bwd(activation, __uint_as_float(v[2 * i]), ff.x),
-                                       act_bwd(activation, __uint_as_float(v[2 * i + 1]), ff.y));
+                        p[i] = pack_h2(act_bwd<ACT>(__uint_as_float(v[2 * i]), ff.x), act_bwd<ACT>(__uint_as_float(v[2 * i + 1]), ff.y));
                     }
 #pragma unroll
                     for (uint32_t c = 0; c < 4; ++c) {
@@ -336,6 +335,215 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
 
     __syncthreads();
     if (warp == 0) tmem_dealloc<64>(tmem_base);
+}
+
+
+// ================================ backward: fused dgrad + wgrad ================================
+// One pass over the batch produces the activation gradients AND the weight gradients: every dPre / H tile is
+// consumed from shared memory by BOTH the next dgrad MMA (K-major view) and the weight-gradient MMA (MN-major view of
+// the same bytes), so backward_buffer never has to be written or re-read (the reference writes it, then re-reads it
+// and forward_buffer in (num_layers+1) separate CUTLASS split-K GEMMs, ffmlp.cu:804-875).
+//   TMEM (256 columns): [0,64) dgrad accumulator (M=128); weight-grad accumulator l (M=64,N=64 fp32, persistent over
+//   the CTA's tiles) at columns 64 + 64*(l/2), lanes +16*(l%2) (two M=64 accumulators interleave in one column range).
+//   smem: G0,G1 (dPre tiles, ping-pong), F0,F1 (forward-activation tiles, ping-pong), transposed weights.
+//   tcgen05.mma executes in issue order, so committing [wgrad(r-1) MMAs, dgrad(r) MMAs] to one mbarrier and waiting for
+//   it orders every buffer reuse.
+// Supports num_layers + 1 <= 6 matmuls (NeRF: 3 and 4); wider nets fall back to the two-kernel path.
+static constexpr uint32_t FUSED_MAX_MATMULS = 6;
+
+__device__ __forceinline__ void issue_wgrad(uint32_t acc_tmem, uint32_t p_addr, uint32_t q_addr, uint32_t accumulate) {
+    const uint32_t idesc = make_idesc(64, 64, 1, 1);
+#pragma unroll
+    for (uint32_t k = 0; k < TILE_M / 16; ++k)
+        mma_f16(acc_tmem, make_desc(p_addr + k * 2048, 16384, 1024, LAYOUT_SW128),
+                make_desc(q_addr + k * 2048, 16384, 1024, LAYOUT_SW128), idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+
+template <uint32_t ACT>
+__global__ void __launch_bounds__(128)
+k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict__ inputs,
+                       const __half* __restrict__ weights, const __half* __restrict__ forward_buffer,
+                       __half* __restrict__ backward_buffer, __half* __restrict__ grad_inputs,
+                       float* __restrict__ wgrad_ws, const uint32_t B, const uint32_t in_dim, const uint32_t num_layers) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+    const uint32_t base = align1024(smem_u32(smem_dyn));
+    unsigned char* base_gen = smem_dyn + (base - smem_u32(smem_dyn));
+    const uint32_t g_addr[2] = {base, base + A_TILE_BYTES};
+    const uint32_t f_addr[2] = {base + 2 * A_TILE_BYTES, base + 3 * A_TILE_BYTES};
+    const uint32_t w_off = 4 * A_TILE_BYTES;
+    const uint32_t w_addr = base + w_off;
+    const uint32_t n_hidden = num_layers - 1;
+    const uint32_t nmat = num_layers + 1;
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+    {   // transposed weights in consumption order (see k_ffmlp_backward)
+        const __half* w0 = weights;
+        const __half* wh = weights + HID * in_dim;
+        const __half* wout = wh + (size_t)n_hidden * HID * HID;
+        load_tile_transposed(base_gen, w_off, wout, OUT_PAD, HID, tid, 128);
+        for (uint32_t j = 0; j < n_hidden; ++j)
+            load_tile_transposed(base_gen, w_off + (1 + j) * W_SLOT_BYTES, wh + (size_t)(n_hidden - 1 - j) * HID * HID, HID, HID, tid, 128);
+        if (grad_inputs) load_tile_transposed(base_gen, w_off + (1 + n_hidden) * W_SLOT_BYTES, w0, HID, in_dim, tid, 128);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
+    // weight-gradient accumulator of matmul l (l = 0 .. nmat-1, weights' order)
+    auto acc_addr = [&](uint32_t l) { return tmem_base + 64u + 64u * (l >> 1) + ((16u * (l & 1u)) << 16); };
+    uint32_t phase = 0;
+    bool first_tile = true;
+
+    const uint32_t ntiles = B / TILE_M;
+    const uint32_t nrounds = 1 + n_hidden + (grad_inputs ? 1u : 0u);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t row0 = (size_t)tile * TILE_M;
+        const size_t row = row0 + tid;
+        // dL/dy -> G1 (K-major A of round 0 and, zero-padded to 64 columns, MN-major operand of the output-layer wgrad)
+        load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128);
+        zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
+
+        // round r consumes A = (r == 0 ? G1 : G[(r-1)&1]) and produces dPre of hidden layer (num_layers-1-r) in G[r&1],
+        // with the matching forward activations H in F[r&1].
+        for (uint32_t r = 0; r < nrounds; ++r) {
+            const bool to_inputs = grad_inputs && (r == nrounds - 1);
+            const uint32_t K = (r == 0) ? OUT_PAD : HID;
+            const uint32_t N = to_inputs ? in_dim : HID;
+            const uint32_t a_in = (r == 0) ? g_addr[1] : g_addr[(r - 1) & 1u];
+            // prefetch this round's forward activations (ReLU mask + wgrad operand) while the MMAs run
+            uint4 f[8];
+            if (!to_inputs) {
+                const uint4* fwd = reinterpret_cast<const uint4*>(forward_buffer + ((size_t)(num_layers - 1 - r) * B + row) * HID);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) f[c] = __ldg(fwd + c);
+            }
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            if (warp == 0) {
+                if (tid == 0) {
+                    fence_after_sync();
+                    // weight gradient of the matmul consumed in the PREVIOUS round: its dPre and H tiles are complete now
+                    if (r == 1) {          // output layer: P = dY (G1, 16 valid columns), Q = H_{nl-1} (F0)
+                        issue_wgrad(acc_addr(nmat - 1), g_addr[1], f_addr[0], first_tile ? 0u : 1u);
+                    } else if (r >= 2) {   // hidden matmul (num_layers+1-r): P = dPre (G[(r-2)&1]), Q = H (F[(r-1)&1])
+                        issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) & 1u], first_tile ? 0u : 1u);
+                    }
+                    issue_layer(tmem_base, a_in, w_addr + r * W_SLOT_BYTES, N, K);
+                    mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            fence_after_sync();
+
+            if (!to_inputs) {
+                const uint32_t gw = g_addr[r & 1u], fw = f_addr[r & 1u];
+                uint4* bb = backward_buffer ? reinterpret_cast<uint4*>(backward_buffer + ((size_t)r * B + row) * HID) : nullptr;
+#pragma unroll
+                for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + half_i * 32, v);
+                    tmem_ld_wait();
+                    const __half2* fh = reinterpret_cast<const __half2*>(&f[half_i * 4]);
+                    uint32_t p[16];
+#pragma unroll
+                    for (uint32_t i = 0; i < 16; ++i) {
+                        const float2 ff = __half22float2(fh[i]);
+                        p[i] = pack_h2(act_bwd<ACT>(__uint_as_float(v[2 * i]), ff.x), act_bwd<ACT>(__uint_as_float(v[2 * i + 1]), ff.y));
+                    }
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) {
+                        const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
+                        st_shared_v4(gw + sw128_off(tid, half_i * 4 + c), q);
+                        st_shared_v4(fw + sw128_off(tid, half_i * 4 + c), f[half_i * 4 + c]);
+                        if (bb) bb[half_i * 4 + c] = q;
+                    }
+                }
+            } else {
+                __half* gi = grad_inputs + row * in_dim;
+                for (uint32_t c0 = 0; c0 < in_dim; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(t_lane + c0, v);
+                    tmem_ld_wait();
+                    uint32_t p[8];
+#pragma unroll
+                    for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                    uint4* o = reinterpret_cast<uint4*>(gi + c0);
+                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                }
+            }
+        }
+
+        // tail of the tile: wgrad of the last hidden matmul handled above (if any) and of matmul 0 (P = dPre_0, Q = X).
+        // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden & 1]; X goes to the other F.
+        {
+            const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
+            load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128);
+            zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            if (warp == 0) {
+                if (tid == 0) {
+                    fence_after_sync();
+                    if (!grad_inputs) {
+                        // the wgrad that the (absent) input round would have issued: matmul 1 (or the output layer when n_hidden == 0)
+                        const uint32_t r = nrounds;   // == 1 + n_hidden
+                        if (r == 1) issue_wgrad(acc_addr(nmat - 1), g_addr[1], f_addr[0], first_tile ? 0u : 1u);
+                        else issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) & 1u], first_tile ? 0u : 1u);
+                    }
+                    issue_wgrad(acc_addr(0), g_addr[n_hidden & 1u], xq, first_tile ? 0u : 1u);
+                    mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            fence_after_sync();
+        }
+        first_tile = false;
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+    }
+
+    // flush the CTA's weight-gradient accumulators (fp32) into the workspace laid out like `weights`
+    if (!first_tile) {
+        for (uint32_t lp = 0; lp < (nmat + 1) / 2; ++lp) {
+            const uint32_t l = lp * 2 + (lane >> 4);                  // lanes 0-15: even matmul, 16-31: odd matmul
+            const uint32_t m = warp * 16 + (lane & 15u);
+            uint32_t Mv, Nv, ws_off;
+            if (l == 0) { Mv = HID; Nv = in_dim; ws_off = 0; }
+            else if (l < nmat - 1) { Mv = HID; Nv = HID; ws_off = HID * in_dim + (l - 1) * HID * HID; }
+            else { Mv = OUT_PAD; Nv = HID; ws_off = HID * in_dim + (num_layers - 1) * HID * HID; }
+#pragma unroll
+            for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + 64u + 64u * lp + half_i * 32, v);
+                tmem_ld_wait();
+                if (l < nmat && m < Mv) {
+                    float* dst = wgrad_ws + ws_off + (size_t)m * Nv;
+#pragma unroll
+                    for (uint32_t i = 0; i < 32; ++i) {
+                        const uint32_t n = half_i * 32 + i;
+                        if (n < Nv) atomicAdd(dst + n, __uint_as_float(v[i]));
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 // ================================ backward: weight gradients ===================================
@@ -533,6 +741,32 @@ static uint32_t persistent_grid(uint32_t ntiles, uint32_t ctas_per_sm) {
 
 using namespace ngp;
 
+#define NGP_DISPATCH_ACT(ACTV, ...)                         \
+    switch (ACTV) {                                         \
+        case ACT_RELU: { constexpr uint32_t A = ACT_RELU; __VA_ARGS__; } break;             \
+        case ACT_EXP: { constexpr uint32_t A = ACT_EXP; __VA_ARGS__; } break;               \
+        case ACT_SINE: { constexpr uint32_t A = ACT_SINE; __VA_ARGS__; } break;             \
+        case ACT_SIGMOID: { constexpr uint32_t A = ACT_SIGMOID; __VA_ARGS__; } break;       \
+        case ACT_SQUAREPLUS: { constexpr uint32_t A = ACT_SQUAREPLUS; __VA_ARGS__; } break; \
+        case ACT_SOFTPLUS: { constexpr uint32_t A = ACT_SOFTPLUS; __VA_ARGS__; } break;     \
+        default: { constexpr uint32_t A = ACT_NONE; __VA_ARGS__; } break;                   \
+    }
+
+template <bool TRAIN>
+static int launch_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t num_layers,
+                          uint32_t activation, void* forward_buffer, void* outputs, cudaStream_t st, const char* who) {
+    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
+    const uint32_t grid = persistent_grid(B / TILE_M, 4);
+    int rc = NGP_OK;
+    NGP_DISPATCH_ACT(activation,
+        rc = set_smem(k_ffmlp_forward<TRAIN, A>, smem, who);
+        if (rc == NGP_OK)
+            k_ffmlp_forward<TRAIN, A><<<grid, 128, smem, st>>>((const __half*)inputs, (const __half*)weights,
+                                                                (__half*)forward_buffer, (__half*)outputs, B, input_dim, num_layers))
+    if (rc) return rc;
+    return check_launch(who);
+}
+
 extern "C" int ngp_ffmlp_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim,
                                  uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
                                  uint32_t output_activation, void* forward_buffer, void* outputs, ngp_stream_t stream) {
@@ -540,14 +774,7 @@ extern "C" int ngp_ffmlp_forward(const void* inputs, const void* weights, uint32
     int rc = check_cfg("ffmlp_forward", B, input_dim, output_dim, hidden_dim, num_layers, output_activation);
     if (rc) return rc;
     if (!forward_buffer) return fail(NGP_EINVAL, "ffmlp_forward: forward_buffer is required (use ffmlp_inference otherwise)");
-    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
-    rc = set_smem(k_ffmlp_forward<true>, smem, "ffmlp_forward");
-    if (rc) return rc;
-    const uint32_t grid = persistent_grid(B / TILE_M, 4);
-    k_ffmlp_forward<true><<<grid, 128, smem, as_stream(stream)>>>((const __half*)inputs, (const __half*)weights,
-                                                                   (__half*)forward_buffer, (__half*)outputs, B,
-                                                                   input_dim, num_layers, activation);
-    return check_launch("ffmlp_forward");
+    return launch_forward<true>(inputs, weights, B, input_dim, num_layers, activation, forward_buffer, outputs, as_stream(stream), "ffmlp_forward");
 }
 
 extern "C" int ngp_ffmlp_inference(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim,
@@ -558,13 +785,7 @@ extern "C" int ngp_ffmlp_inference(const void* inputs, const void* weights, uint
     if (B == 0) return NGP_OK;
     int rc = check_cfg("ffmlp_inference", B, input_dim, output_dim, hidden_dim, num_layers, output_activation);
     if (rc) return rc;
-    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
-    rc = set_smem(k_ffmlp_forward<false>, smem, "ffmlp_inference");
-    if (rc) return rc;
-    const uint32_t grid = persistent_grid(B / TILE_M, 4);
-    k_ffmlp_forward<false><<<grid, 128, smem, as_stream(stream)>>>((const __half*)inputs, (const __half*)weights, nullptr,
-                                                                    (__half*)outputs, B, input_dim, num_layers, activation);
-    return check_launch("ffmlp_inference");
+    return launch_forward<false>(inputs, weights, B, input_dim, num_layers, activation, nullptr, outputs, as_stream(stream), "ffmlp_inference");
 }
 
 extern "C" size_t ngp_ffmlp_backward_workspace_bytes(uint32_t B, uint32_t input_dim, uint32_t output_dim,
@@ -573,6 +794,7 @@ extern "C" size_t ngp_ffmlp_backward_workspace_bytes(uint32_t B, uint32_t input_
     return sizeof(float) * (size_t)hidden_dim * (input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim);
 }
 
+// backward_buffer may be NULL: the fused kernel then keeps dL/d(pre-activation) on chip only.
 extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const void* weights, const void* forward_buffer,
                                   uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
                                   uint32_t num_layers, uint32_t activation, uint32_t output_activation,
@@ -586,22 +808,38 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
     cudaStream_t st = as_stream(stream);
     const uint32_t n_params = (uint32_t)(need / sizeof(float));
     if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return fail(NGP_ECUDA, "ffmlp_backward: memset failed");
-    if (B > 0) {
+    const uint32_t nmat = num_layers + 1;
+    __half* gi = calc_grad_inputs ? (__half*)grad_inputs : nullptr;
+    if (B > 0 && nmat <= FUSED_MAX_MATMULS) {
+        const uint32_t nslots = 1 + (num_layers - 1) + (calc_grad_inputs ? 1 : 0);
+        const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
+        const uint32_t grid = persistent_grid(B / TILE_M, 2);
+        NGP_DISPATCH_ACT(activation,
+            rc = set_smem(k_ffmlp_backward_fused<A>, smem, "ffmlp_backward");
+            if (rc == NGP_OK)
+                k_ffmlp_backward_fused<A><<<grid, 128, smem, st>>>((const __half*)grad, (const __half*)inputs, (const __half*)weights,
+                                                                   (const __half*)forward_buffer, (__half*)backward_buffer, gi,
+                                                                   (float*)workspace, B, input_dim, num_layers))
+        if (rc) return rc;
+        rc = check_launch("ffmlp_backward");
+        if (rc) return rc;
+    } else if (B > 0) {
+        if (!backward_buffer) return fail(NGP_EINVAL, "ffmlp_backward: backward_buffer is required for num_layers > 5");
         const uint32_t nslots = 1 + (num_layers - 1) + (calc_grad_inputs ? 1 : 0);
         const size_t smem = 1024 + A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
-        rc = set_smem(k_ffmlp_backward, smem, "ffmlp_backward");
-        if (rc) return rc;
         const uint32_t grid = persistent_grid(B / TILE_M, 4);
-        k_ffmlp_backward<<<grid, 128, smem, st>>>((const __half*)grad, (const __half*)weights, (const __half*)forward_buffer,
-                                                  (__half*)backward_buffer, calc_grad_inputs ? (__half*)grad_inputs : nullptr,
-                                                  B, input_dim, num_layers, activation);
+        NGP_DISPATCH_ACT(activation,
+            rc = set_smem(k_ffmlp_backward<A>, smem, "ffmlp_backward");
+            if (rc == NGP_OK)
+                k_ffmlp_backward<A><<<grid, 128, smem, st>>>((const __half*)grad, (const __half*)weights, (const __half*)forward_buffer,
+                                                             (__half*)backward_buffer, gi, B, input_dim, num_layers))
+        if (rc) return rc;
         rc = check_launch("ffmlp_backward");
         if (rc) return rc;
 
         const size_t smem_w = 1024 + 2 * (size_t)WG_STAGE_BYTES;
         rc = set_smem(k_ffmlp_wgrad, smem_w, "ffmlp_backward(wgrad)");
         if (rc) return rc;
-        const uint32_t nmat = num_layers + 1;
         const uint32_t ntiles = B / TILE_M;
         uint32_t nsplit = (uint32_t)sm_count() * 2 / nmat;
         if (nsplit < 1) nsplit = 1;

@@ -55,13 +55,16 @@ class _ffmlp_forward(Function):
 
         grad_inputs = torch.empty_like(inputs) if calc_grad_inputs else None
         grad_weights = torch.empty_like(weights)
-        backward_buffer = torch.empty(num_layers, B, hidden_dim, device=grad.device, dtype=grad.dtype)
+        # the fused dgrad+wgrad kernel keeps dL/d(pre-activation) on chip; only nets deeper than 5 hidden layers
+        # (two-kernel fallback) need the reference's [num_layers, B, hidden] scratch in HBM
+        backward_buffer = (torch.empty(num_layers, B, hidden_dim, device=grad.device, dtype=grad.dtype)
+                           if num_layers + 1 > 6 else None)
         ws_bytes = _backend.load().ngp_ffmlp_backward_workspace_bytes(B, input_dim, output_dim, hidden_dim, num_layers)
         workspace = torch.empty(ws_bytes // 4, device=grad.device, dtype=torch.float32)
 
         _backend.call("ngp_ffmlp_backward", grad.data_ptr(), inputs.data_ptr(), weights.data_ptr(),
                       forward_buffer.data_ptr(), B, input_dim, output_dim, hidden_dim, num_layers, activation,
-                      output_activation, int(calc_grad_inputs), backward_buffer.data_ptr(),
+                      output_activation, int(calc_grad_inputs), _backend.ptr(backward_buffer),
                       _backend.ptr(grad_inputs), grad_weights.data_ptr(), workspace.data_ptr(), ws_bytes)
 
         if calc_grad_inputs:
