@@ -141,7 +141,7 @@ if __name__ == "__main__":
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     model, _ = bench.build_model(dev)
-    _, dev_in = bench.make_inputs(a.rays_per_step, 0, a.rays_per_step, dev)
+    _, dev_in = bench.make_inputs(a.rays_per_step, 0, 1, dev)
     # steady-state sample budget, measured with the reference marcher itself
     nears, fars = R.near_far_from_aabb(dev_in[0][0], dev_in[0][1], model.aabb_train, model.min_near)
     counts = []

@@ -81,7 +81,7 @@ int ngp_sh_encode_backward(const float* grad, const float* inputs, uint32_t B, u
 /* ---- ffmlp  (ffmlp/src/ffmlp.h:8-14) ------------------------------------------------------- */
 /* All tensors fp16, row-major.  inputs [B,input_dim]; weights = [hidden,input_dim] then
  * (num_layers-1) x [hidden,hidden] then [output_dim,hidden], each [out,in] row-major
- * (ffmlp.cu:631-634).  B must be a multiple of 128 (ffmlp.py:157-159 pads).  hidden_dim == 64,
+ * (ffmlp.cu:631-634).  Any B >= 0 (the ragged last 128-row tile is masked in-kernel; the reference pads, ffmlp.py:157-159).  hidden_dim == 64,
  * input_dim in {16,32,48,64}, output_dim == 16 in this build; activation codes as
  * ffmlp.py:89-96 (0 = ReLU ... 6 = None); output_activation must be 6 (ffmlp.py:108).
  * forward_buffer [num_layers,B,hidden] receives every hidden activation (training). */

@@ -68,13 +68,15 @@ __device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) &
 
 // copy a row-major [rows x cols] fp16 matrix (cols % 8 == 0) from global into a swizzled tile,
 // 16-byte chunks, coalesced along the source rows.
+// rows >= rows_valid (ragged last batch tile) are filled with zeros.
 __device__ __forceinline__ void load_tile_rowmajor(uint32_t tile_addr, const __half* __restrict__ src, uint32_t rows,
-                                                   uint32_t cols, uint32_t tid, uint32_t nthr) {
+                                                   uint32_t cols, uint32_t tid, uint32_t nthr, uint32_t rows_valid = 0xffffffffu) {
     const uint32_t cpr = cols >> 3;
     const uint32_t total = rows * cpr;
     for (uint32_t g = tid; g < total; g += nthr) {
         const uint32_t r = g / cpr, c = g - r * cpr;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * cols) + c);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * cols) + c);
         st_shared_v4(tile_addr + sw128_off(r, c), v);
     }
 }
@@ -147,12 +149,14 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
     const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
     uint32_t phase = 0;
 
-    const uint32_t ntiles = B / TILE_M;
+    const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
+        const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
+        const bool row_ok = tid < rows_valid;
         // input tile -> A operand
-        load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128);
+        load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
 
         for (uint32_t l = 0; l < nmat; ++l) {
             const bool last = (l == nmat - 1);
@@ -190,7 +194,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
                     for (uint32_t c = 0; c < 4; ++c) {
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                         st_shared_v4(a_addr + sw128_off(tid, half_i * 4 + c), q);
-                        if (TRAIN) reinterpret_cast<uint4*>(fb)[half_i * 4 + c] = q;
+                        if (TRAIN && row_ok) reinterpret_cast<uint4*>(fb)[half_i * 4 + c] = q;
                     }
                 }
             } else {
@@ -200,9 +204,11 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
                 uint32_t p[8];
 #pragma unroll
                 for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                uint4* o = reinterpret_cast<uint4*>(outputs + row * OUT_PAD);
-                o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                if (row_ok) {
+                    uint4* o = reinterpret_cast<uint4*>(outputs + row * OUT_PAD);
+                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                }
             }
         }
         // the next tile's input load overwrites the A tile: every warp must be done reading TMEM /
@@ -260,12 +266,14 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
     const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
     uint32_t phase = 0;
 
-    const uint32_t ntiles = B / TILE_M;
+    const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     const uint32_t nrounds = 1 + n_hidden + (grad_inputs ? 1u : 0u);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
-        load_tile_rowmajor(a_addr, grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128);
+        const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
+        const bool row_ok = tid < rows_valid;
+        load_tile_rowmajor(a_addr, grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128, rows_valid);
 
         for (uint32_t r = 0; r < nrounds; ++r) {
             const bool to_inputs = grad_inputs && (r == nrounds - 1);
@@ -297,7 +305,7 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
                     tmem_ld32(t_lane + half_i * 32, v);
                     uint4 f[4];
 #pragma unroll
-                    for (uint32_t c = 0; c < 4; ++c) f[c] = __ldg(fwd + half_i * 4 + c);
+                    for (uint32_t c = 0; c < 4; ++c) f[c] = row_ok ? __ldg(fwd + half_i * 4 + c) : make_uint4(0, 0, 0, 0);
                     tmem_ld_wait();
                     const __half2* fh = reinterpret_cast<const __half2*>(f);
                     uint32_t p[16];
@@ -310,7 +318,7 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
                     for (uint32_t c = 0; c < 4; ++c) {
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                         st_shared_v4(a_addr + sw128_off(tid, half_i * 4 + c), q);
-                        bb[half_i * 4 + c] = q;
+                        if (row_ok) bb[half_i * 4 + c] = q;
                     }
                 }
             } else {
@@ -322,9 +330,11 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
                     uint32_t p[8];
 #pragma unroll
                     for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                    uint4* o = reinterpret_cast<uint4*>(gi + c0);
-                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    if (row_ok) {
+                        uint4* o = reinterpret_cast<uint4*>(gi + c0);
+                        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    }
                 }
             }
         }
@@ -400,13 +410,15 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
     uint32_t phase = 0;
     bool first_tile = true;
 
-    const uint32_t ntiles = B / TILE_M;
+    const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     const uint32_t nrounds = 1 + n_hidden + (grad_inputs ? 1u : 0u);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
+        const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
+        const bool row_ok = tid < rows_valid;
         // dL/dy -> G1 (K-major A of round 0 and, zero-padded to 64 columns, MN-major operand of the output-layer wgrad)
-        load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128);
+        load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128, rows_valid);
         zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
 
         // round r consumes A = (r == 0 ? G1 : G[(r-1)&1]) and produces dPre of hidden layer (num_layers-1-r) in G[r&1],
@@ -421,7 +433,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             if (!to_inputs) {
                 const uint4* fwd = reinterpret_cast<const uint4*>(forward_buffer + ((size_t)(num_layers - 1 - r) * B + row) * HID);
 #pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) f[c] = __ldg(fwd + c);
+                for (uint32_t c = 0; c < 8; ++c) f[c] = row_ok ? __ldg(fwd + c) : make_uint4(0, 0, 0, 0);
             }
             fence_async_smem();
             fence_before_sync();
@@ -464,7 +476,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                         st_shared_v4(gw + sw128_off(tid, half_i * 4 + c), q);
                         st_shared_v4(fw + sw128_off(tid, half_i * 4 + c), f[half_i * 4 + c]);
-                        if (bb) bb[half_i * 4 + c] = q;
+                        if (bb && row_ok) bb[half_i * 4 + c] = q;
                     }
                 }
             } else {
@@ -476,9 +488,11 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                     uint32_t p[8];
 #pragma unroll
                     for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                    uint4* o = reinterpret_cast<uint4*>(gi + c0);
-                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    if (row_ok) {
+                        uint4* o = reinterpret_cast<uint4*>(gi + c0);
+                        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    }
                 }
             }
         }
@@ -487,7 +501,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden & 1]; X goes to the other F.
         {
             const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
-            load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128);
+            load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
             zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             fence_async_smem();
             fence_before_sync();
@@ -596,7 +610,7 @@ k_ffmlp_wgrad(const __half* __restrict__ grad, const __half* __restrict__ inputs
     const uint32_t tmem_base = tmem_base_s;
 
     const uint32_t idesc = make_idesc(64, 64, 1, 1);   // both operands MN-major
-    const uint32_t ntiles = B / TILE_M;
+    const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     uint32_t ph[2] = {0, 0};
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.y; tile < ntiles; tile += gridDim.y, ++it) {
@@ -604,8 +618,9 @@ k_ffmlp_wgrad(const __half* __restrict__ grad, const __half* __restrict__ inputs
         const uint32_t p_addr = base + s * WG_STAGE_BYTES, q_addr = p_addr + A_TILE_BYTES;
         if (it >= 2) { mbar_wait(&bars[s], ph[s]); ph[s] ^= 1u; }   // MMAs that read this stage are done
         const size_t row0 = (size_t)tile * TILE_M;
-        load_tile_rowmajor(p_addr, P + row0 * Pw, TILE_M, Pw, tid, 128);
-        load_tile_rowmajor(q_addr, Q + row0 * Qw, TILE_M, Qw, tid, 128);
+        const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
+        load_tile_rowmajor(p_addr, P + row0 * Pw, TILE_M, Pw, tid, 128, rows_valid);
+        load_tile_rowmajor(q_addr, Q + row0 * Qw, TILE_M, Qw, tid, 128, rows_valid);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -720,7 +735,6 @@ static int check_cfg(const char* who, uint32_t B, uint32_t input_dim, uint32_t o
         return fail(NGP_EUNSUPPORTED, "%s: input_dim must be 16, 32, 48 or 64 (got %u)", who, input_dim);
     if (output_dim != OUT_PAD) return fail(NGP_EUNSUPPORTED, "%s: padded output_dim must be 16 (got %u)", who, output_dim);
     if (num_layers < 2 || num_layers + 1 > MAX_MATMULS) return fail(NGP_EINVAL, "%s: num_layers must be in [2, 8] (got %u)", who, num_layers);
-    if (B % TILE_M != 0) return fail(NGP_EINVAL, "%s: batch size must be a multiple of 128 (got %u)", who, B);
     if (output_activation != ACT_NONE) return fail(NGP_EUNSUPPORTED, "%s: output activation is not supported (ffmlp.py:108)", who);
     return NGP_OK;
 }
@@ -756,7 +770,7 @@ template <bool TRAIN>
 static int launch_forward(const void* inputs, const void* weights, uint32_t B, uint32_t input_dim, uint32_t num_layers,
                           uint32_t activation, void* forward_buffer, void* outputs, cudaStream_t st, const char* who) {
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
-    const uint32_t grid = persistent_grid(B / TILE_M, 4);
+    const uint32_t grid = persistent_grid((B + TILE_M - 1) / TILE_M, 4);
     int rc = NGP_OK;
     NGP_DISPATCH_ACT(activation,
         rc = set_smem(k_ffmlp_forward<TRAIN, A>, smem, who);
@@ -813,7 +827,7 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
     if (B > 0 && nmat <= FUSED_MAX_MATMULS) {
         const uint32_t nslots = 1 + (num_layers - 1) + (calc_grad_inputs ? 1 : 0);
         const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
-        const uint32_t grid = persistent_grid(B / TILE_M, 2);
+        const uint32_t grid = persistent_grid((B + TILE_M - 1) / TILE_M, 2);
         NGP_DISPATCH_ACT(activation,
             rc = set_smem(k_ffmlp_backward_fused<A>, smem, "ffmlp_backward");
             if (rc == NGP_OK)
@@ -827,7 +841,7 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
         if (!backward_buffer) return fail(NGP_EINVAL, "ffmlp_backward: backward_buffer is required for num_layers > 5");
         const uint32_t nslots = 1 + (num_layers - 1) + (calc_grad_inputs ? 1 : 0);
         const size_t smem = 1024 + A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
-        const uint32_t grid = persistent_grid(B / TILE_M, 4);
+        const uint32_t grid = persistent_grid((B + TILE_M - 1) / TILE_M, 4);
         NGP_DISPATCH_ACT(activation,
             rc = set_smem(k_ffmlp_backward<A>, smem, "ffmlp_backward");
             if (rc == NGP_OK)
@@ -840,7 +854,7 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
         const size_t smem_w = 1024 + 2 * (size_t)WG_STAGE_BYTES;
         rc = set_smem(k_ffmlp_wgrad, smem_w, "ffmlp_backward(wgrad)");
         if (rc) return rc;
-        const uint32_t ntiles = B / TILE_M;
+        const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
         uint32_t nsplit = (uint32_t)sm_count() * 2 / nmat;
         if (nsplit < 1) nsplit = 1;
         if (nsplit > ntiles) nsplit = ntiles;

@@ -1,9 +1,9 @@
 """ffmlp — drop-in for the reference's ffmlp/ffmlp.py (FFMLP :99-168, _ffmlp_forward :15-83).
 
 Same constructor, parameter layout (`weights`: one flat fp32 vector of [out,in] row-major matrices,
-ffmlp.cu:631-634), same init (global seed 42 + U(+-sqrt(3/hidden)), ffmlp.py:141-144) and the same
-padding rules (batch padded to a multiple of 128 — a full extra tile when already aligned,
-ffmlp.py:157-159; output padded to 16).  Underneath: the tcgen05/TMEM kernels of csrc/ffmlp.cu via the
+ffmlp.cu:631-634), same init (global seed 42 + U(+-sqrt(3/hidden)), ffmlp.py:141-144), output padded to 16
+(ffmlp.py:118).  The reference's batch padding to a multiple of 128 (ffmlp.py:157-159, a cat-copy of the input) is
+internal to it and replaced by in-kernel masking of the ragged last tile.  Underneath: the tcgen05/TMEM kernels of csrc/ffmlp.cu via the
 C-ABI.  The stray `from turtle import ...` of the reference (ffmlp.py:2) is deliberately not reproduced.
 """
 import math
@@ -128,11 +128,8 @@ class FFMLP(nn.Module):
     def forward(self, inputs):
         # inputs: [B, input_dim] -> [B, output_dim]
         B, C = inputs.shape
-        # pad batch to a multiple of 128 (always adds >= 1 row, like the reference)
-        pad = 128 - (B % 128)
-        if pad > 0:
-            inputs = torch.cat([inputs, torch.zeros(pad, C, dtype=inputs.dtype, device=inputs.device)], dim=0)
-
+        # The reference pads the batch to a multiple of 128 with a torch.cat copy of the whole input (ffmlp.py:157-159).
+        # The tcgen05 kernels mask the ragged last tile themselves, so no copy is made; results are identical.
         outputs = ffmlp_forward(inputs, self.weights, self.input_dim, self.padded_output_dim, self.hidden_dim,
                                 self.num_layers, self.activation, self.output_activation, not self.training,
                                 inputs.requires_grad)

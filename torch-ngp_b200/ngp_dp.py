@@ -18,6 +18,14 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_indices(n, rank, world, block=256):
+    """Round-robin blocks of `block` rays: rank r owns blocks r, r+world, ...  Balances per-rank sample counts (a
+    contiguous split of an image gives one rank the sky and another the object)."""
+    idx = torch.arange(n)
+    blk = idx // block
+    return idx[blk % world == rank]
+
+
 class FlatGradBucket:
     def __init__(self, params, dtype=torch.float32):
         self.params = [p for p in params if p.requires_grad]
