@@ -56,6 +56,57 @@ __device__ __forceinline__ float level_scale(uint32_t level, float S, uint32_t H
     return fmaf(exp2f(level * S), (float)H, -1.0f);
 }
 
+// All 2^D corner entry indices of one (point, level) at once.  Same results as level_index() (the reference's
+// get_grid_index, gridencoder.cu:66-84) but the level's addressing mode is decided once per warp:
+//   dense  : every stride fits ((res+1)^D <= size)  -> base + constant corner offsets, no modulo needed
+//   hash^2 : hashed level with a power-of-two table  -> per-dim products once, xor + mask per corner
+//   generic: anything else (tiled wrap-around, non-power-of-two hashed sizes) -> reference loop
+template <uint32_t D>
+__device__ __forceinline__ void corner_indices(uint32_t gridtype, bool align_corners, uint32_t hashmap_size,
+                                               uint32_t resolution, const uint32_t pg[D], uint32_t out[1u << D]) {
+    const uint32_t r1 = align_corners ? resolution : resolution + 1;
+    // does the dense index space fit?  (64-bit so (res+1)^D cannot wrap)
+    unsigned long long cells = 1;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) cells = cells * r1 > 0xffffffffull ? 0x100000000ull : cells * r1;
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    if (cells <= hashmap_size) {
+        uint32_t stride[D], base = 0, st = 1;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) { stride[d] = st; base += pg[d] * st; st *= r1; }
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t v = base;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) if (idx & (1u << d)) v += stride[d];
+            out[idx] = v;
+        }
+    } else if (gridtype == 0 && (hashmap_size & (hashmap_size - 1)) == 0) {
+        // NOTE: the reference hashes only if the stride product overflowed the table, which is exactly cells > size
+        uint32_t h0[D], h1[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) { h0[d] = pg[d] * primes[d]; h1[d] = h0[d] + primes[d]; }
+        const uint32_t mask = hashmap_size - 1;
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t v = 0;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) v ^= (idx & (1u << d)) ? h1[d] : h0[d];
+            out[idx] = v & mask;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) pl[d] = pg[d] + ((idx >> d) & 1u);
+            out[idx] = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+        }
+    }
+}
+
+__device__ __forceinline__ float corner_weight_1(bool hi, float p) { return hi ? p : 1 - p; }
+
 // ---- accumulate / load / store helpers per table dtype --------------------------------------
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
@@ -63,6 +114,13 @@ template <typename T> __device__ __forceinline__ T from_f(float v);
 template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
+// two channels at once: fp32 products, one cvt.rn.f16x2.f32, one HADD2.  Bit-identical to the scalar sequence
+// half(float(r) + float(half(w*g))): the sum of two fp16 values is exact in fp32 unless the smaller one is below a
+// quarter ulp of the larger, in which case both roundings return the larger operand.
+__device__ __forceinline__ void acc2(__half2& r, float w, __half2 g) {
+    const float2 gf = __half22float2(g);
+    r = __hadd2(r, __floats2half2_rn(w * gf.x, w * gf.y));
+}
 __device__ __forceinline__ void acc(float& r, float w, float g) { r = fmaf(w, g, r); }
 __device__ __forceinline__ void acc(__half& r, float w, __half g) {
     const __half p = __float2half_rn(w * __half2float(g));
@@ -159,23 +217,30 @@ k_grid_forward(const float* __restrict__ inputs, const T* __restrict__ table,
                 // reference's corner order (idx bit d selects +1 along dim d).
                 T val[1 << D][C];
                 float wgt[1 << D];
+                uint32_t cidx[1 << D];
+                corner_indices<D>(gridtype, align_corners, hashmap_size, resolution, pg, cidx);
+#pragma unroll
+                for (uint32_t idx = 0; idx < (1u << D); ++idx) load_entry<T, C>(lvl + (size_t)cidx[idx] * C, val[idx]);
 #pragma unroll
                 for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-                    float w = 1;
-                    uint32_t pl[D];
+                    float w = 1;     // same multiplication order as the reference: ((1*a0)*a1)*a2
 #pragma unroll
-                    for (uint32_t d = 0; d < D; ++d) {
-                        if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
-                        else                        { w *= pos[d];     pl[d] = pg[d] + 1; }
-                    }
+                    for (uint32_t d = 0; d < D; ++d) w *= ((idx & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
                     wgt[idx] = w;
-                    const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
-                    load_entry<T, C>(lvl + (size_t)index * C, val[idx]);
                 }
+                if constexpr (sizeof(T) == 2 && C % 2 == 0) {
+                    __half2* r2 = reinterpret_cast<__half2*>(res);
 #pragma unroll
-                for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+                    for (uint32_t idx = 0; idx < (1u << D); ++idx) {
 #pragma unroll
-                    for (uint32_t c = 0; c < C; ++c) acc(res[c], wgt[idx], val[idx][c]);
+                        for (uint32_t c = 0; c < C / 2; ++c) acc2(r2[c], wgt[idx], reinterpret_cast<const __half2*>(val[idx])[c]);
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+#pragma unroll
+                        for (uint32_t c = 0; c < C; ++c) acc(res[c], wgt[idx], val[idx][c]);
+                    }
                 }
 
                 if (dy_dx) {
@@ -331,16 +396,14 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
             if (interp == 1) pos[d] = smoothstep_f(pos[d]);
         }
 
+        uint32_t cidx[1 << D];
+        corner_indices<D>(gridtype, align_corners, hashmap_size, resolution, pg, cidx);
 #pragma unroll
         for (uint32_t idx = 0; idx < (1u << D); ++idx) {
             float w = 1;
-            uint32_t pl[D];
 #pragma unroll
-            for (uint32_t d = 0; d < D; ++d) {
-                if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pl[d] = pg[d]; }
-                else                        { w *= pos[d];     pl[d] = pg[d] + 1; }
-            }
-            const uint32_t index = level_index<D>(gridtype, align_corners, hashmap_size, resolution, pl);
+            for (uint32_t d = 0; d < D; ++d) w *= ((idx & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+            const uint32_t index = cidx[idx];
 
             // addends: rounded per sample exactly like the reference when the lane stands alone
             float v[C];
@@ -355,8 +418,9 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
             bool issue = active;
             if (heads != FULL) {
                 const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
-#pragma unroll
-                for (uint32_t o = 1; o < 32; o <<= 1) {
+                // scan only as deep as the longest run in this warp (redux.sync max)
+                const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;
+                for (uint32_t o = 1; o < maxrun; o <<= 1) {
 #pragma unroll
                     for (uint32_t c = 0; c < C; ++c) {
                         const float t = __shfl_up_sync(FULL, v[c], o);
