@@ -145,6 +145,28 @@ int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
                        float* rays_t, const float* sigmas, const float* rgbs, const float* deltas,
                        float* weights_sum, float* depth, float* image, ngp_stream_t stream);
 
+/* ---- fused NeRF-field extensions (no reference counterpart: they fuse GridEncoder -> FFMLP -> trunc_exp and
+ * SHEncoder -> cat -> FFMLP -> sigmoid of nerf/network_ff.py:51-74 so that encoder features, SH features and the
+ * concatenated color input never exist in HBM).  Optional fast path; the reference-shaped ops above remain. ---- */
+/* x01 [M,3] f32 in [0,1]; table fp16; writes h_out [M,16] fp16 (sigma-net output), sigma_out [M] f32 = exp(h[:,0])
+ * (nullable), and when train != 0 the stashes feat_out [M,2L] fp16 and forward_buffer [num_layers,M,64] fp16. */
+int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32_t* offsets, uint32_t L, float S,
+                            uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
+                            uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer,
+                            void* h_out, float* sigma_out, ngp_stream_t stream);
+/* dirs [M,3] f32, h_sigma [M,16] fp16 -> rgb_out [M,3] f32 = sigmoid(color_net([SH4(dir) | h_sigma[:,1:] | 0])[:, :3]) */
+int ngp_field_color_forward(const float* dirs, const void* h_sigma, const void* weights, uint32_t num_layers,
+                            uint32_t M, int train, void* forward_buffer, float* rgb_out, ngp_stream_t stream);
+/* color-net backward incl. sigmoid / cat / trunc_exp gradients: writes dys_out [M,16] fp16 = dL/d(sigma-net output)
+ * and grad_weights (color net).  The sigma net then uses ngp_ffmlp_backward(grad = dys_out, inputs = feat). */
+int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* d_sigma, const void* h_sigma,
+                             const float* dirs, const void* weights, const void* forward_buffer,
+                             uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
+                             size_t workspace_bytes, ngp_stream_t stream);
+/* test hooks (not part of the reference ABI) */
+int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
+int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,10 @@ _SIGNATURES = {
     "ngp_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _sz, _vp],
     "ngp_ffmlp_allocate_splitk": [_sz],
     "ngp_ffmlp_free_splitk": [],
+    "ngp_field_sigma_forward": [_vp, _vp, _vp, _u32, _f32, _u32, _u32, _i32, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "ngp_field_color_forward": [_vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp],
+    "ngp_field_color_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp],
+    "ngp_debug_umma": [_vp, _vp, _vp, _i32, _vp],
     "ngp_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "ngp_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
     "ngp_morton3D": [_vp, _u32, _vp, _vp],

@@ -25,102 +25,173 @@
 //     accumulators persistent across the CTA's row tiles, then one fp32 red.add per element.
 #include "common.cuh"
 #include "umma.cuh"
+#include "mlp_common.cuh"
+#include "grid.cuh"
+#include "sh.cuh"
 
 namespace ngp {
 using namespace umma;
 
-static constexpr uint32_t TILE_M = 128;       // batch rows per CTA tile
-static constexpr uint32_t HID = 64;           // hidden width supported by this build
-static constexpr uint32_t OUT_PAD = 16;       // padded output width (ffmlp.py:118)
-static constexpr uint32_t MAX_MATMULS = 9;    // num_layers + 1 <= 9
-static constexpr uint32_t A_TILE_BYTES = TILE_M * 128;   // 16 KB
-static constexpr uint32_t W_SLOT_BYTES = HID * 128;      // 8 KB per weight matrix slot
-static constexpr float K_ACT = 10.0f;         // reference utils.h: squareplus / softplus sharpness
+// ---- fused field front/back ends -----------------------------------------------------------------
+// The MLP kernels can be fed / drained on chip instead of through HBM tensors:
+//   IN_GRID : the input tile is produced by the hash-grid encoder in the kernel itself (thread = sample, 16 levels
+//             x 8 gathers, same arithmetic as k_grid_forward -> bit-identical features), written straight into the
+//             swizzled A operand tile; the [M,32] feature tensor is only written as a stash for the backward.
+//   IN_SHGEO: the color-net input [SH4(dir) (16) | geo_feat (15) | 0] is assembled in the kernel from the view
+//             directions and the sigma-net output (replaces SHEncoder + torch.cat + half cast, network_ff.py:64-69).
+//   OUT_SIGMA: epilogue writes h [M,16] fp16 and sigma = exp(h[:,0]) fp32 (trunc_exp forward, activation.py:8-11).
+//   OUT_RGB  : epilogue writes rgb = sigmoid(h[:, :3]) (rounded through fp16 like torch.sigmoid on a half tensor).
+enum : int { IN_PLAIN = 0, IN_GRID = 1, IN_SHGEO = 2 };
+enum : int { OUT_PLAIN = 0, OUT_SIGMA = 1, OUT_RGB = 2 };
 
-enum Act : uint32_t { ACT_RELU = 0, ACT_EXP = 1, ACT_SINE = 2, ACT_SIGMOID = 3, ACT_SQUAREPLUS = 4, ACT_SOFTPLUS = 5, ACT_NONE = 6 };
+struct FieldArgs {
+    // IN_GRID
+    const float* xyz;        // [M,3] world coordinates
+    float bound, inv_2bound;
+    const __half* table;     // fp16 hash table
+    const int* offsets;      // [L+1]
+    uint32_t L;
+    float S;
+    uint32_t H;
+    uint32_t gridtype;
+    int align_corners;
+    __half* feat_out;        // [M, 2L] stash (nullable)
+    // IN_SHGEO (and the color backward)
+    const float* dirs;       // [M,3]
+    const __half* h_sigma;   // [M,16]
+    // outputs
+    float* sigma_out;        // [M]
+    float* rgb_out;          // [M,3]
+    // color backward
+    const float* d_rgb;      // [M,3]
+    const float* rgb;        // [M,3] (forward output)
+    const float* d_sigma;    // [M]
+    __half* dys_out;         // [M,16] dL/d(sigma-net output)
+};
 
-// Activations are compile-time template parameters: a runtime switch inlined 64x per thread per layer
-// blew the kernel up to ~570 KB of SASS and made it instruction-fetch bound (ncu r1: 65% of stall samples
-// "no_instructions", tensor pipe 0.9%).
-template <uint32_t A>
-__device__ __forceinline__ float act_fwd(float x) {
-    if constexpr (A == ACT_RELU) return fmaxf(x, 0.f);
-    else if constexpr (A == ACT_EXP) return expf(x);
-    else if constexpr (A == ACT_SINE) return sinf(x);
-    else if constexpr (A == ACT_SIGMOID) return 1.0f / (1.0f + expf(-x));
-    else if constexpr (A == ACT_SQUAREPLUS) { const float t = x * K_ACT; return 0.5f * (t + sqrtf(t * t + 4)) / K_ACT; }
-    else if constexpr (A == ACT_SOFTPLUS) return logf(expf(x * K_ACT) + 1.0f) / K_ACT;
-    else return x;
-}
-// dL/dpre = g * act'(.) expressed through the stored post-activation value f (reference
-// utils.h warp_activation_backward)
-template <uint32_t A>
-__device__ __forceinline__ float act_bwd(float g, float f) {
-    if constexpr (A == ACT_RELU) return f > 0.f ? g : 0.f;
-    else if constexpr (A == ACT_EXP) return g * f;
-    else if constexpr (A == ACT_SIGMOID) return g * (f * (1.0f - f));
-    else if constexpr (A == ACT_SQUAREPLUS) { const float y = f * K_ACT; return g * (y * y / (y * y + 1)); }
-    else if constexpr (A == ACT_SOFTPLUS) return g * (1.0f - expf(-f * K_ACT));
-    else return g;   // None; Sine: the reference leaves the gradient unchanged (needs pre-activations)
-}
-
-__device__ __forceinline__ uint32_t align1024(uint32_t a) { return (a + 1023u) & ~1023u; }
-
-// copy a row-major [rows x cols] fp16 matrix (cols % 8 == 0) from global into a swizzled tile,
-// 16-byte chunks, coalesced along the source rows.
-// rows >= rows_valid (ragged last batch tile) are filled with zeros.
-__device__ __forceinline__ void load_tile_rowmajor(uint32_t tile_addr, const __half* __restrict__ src, uint32_t rows,
-                                                   uint32_t cols, uint32_t tid, uint32_t nthr, uint32_t rows_valid = 0xffffffffu) {
-    const uint32_t cpr = cols >> 3;
-    const uint32_t total = rows * cpr;
-    for (uint32_t g = tid; g < total; g += nthr) {
-        const uint32_t r = g / cpr, c = g - r * cpr;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * cols) + c);
-        st_shared_v4(tile_addr + sw128_off(r, c), v);
-    }
-}
-// zero-fill chunks [c0, 8) of every row of a tile
-__device__ __forceinline__ void zero_tile_cols(uint32_t tile_addr, uint32_t rows, uint32_t c0, uint32_t tid, uint32_t nthr) {
-    const uint32_t cpr = 8 - c0;
-    if (cpr == 0) return;
-    const uint32_t total = rows * cpr;
-    for (uint32_t g = tid; g < total; g += nthr) {
-        const uint32_t r = g / cpr, c = c0 + (g - r * cpr);
-        st_shared_v4(tile_addr + sw128_off(r, c), make_uint4(0, 0, 0, 0));
-    }
-}
-// store the TRANSPOSE of a row-major [k_rows x n_cols] matrix: tile(n, k) = src[k][n]
-__device__ __forceinline__ void load_tile_transposed(unsigned char* smem_generic, uint32_t tile_off,
-                                                     const __half* __restrict__ src, uint32_t k_rows, uint32_t n_cols,
-                                                     uint32_t tid, uint32_t nthr) {
-    const uint32_t total = k_rows * n_cols;
-    for (uint32_t g = tid; g < total; g += nthr) {
-        const uint32_t k = g / n_cols, n = g - k * n_cols;
-        const __half v = src[g];
-        *reinterpret_cast<__half*>(smem_generic + tile_off + sw128_off(n, k >> 3) + ((k & 7u) << 1)) = v;
+// degree-4 real SH of one direction, fp32 (same recurrence as k_sh_forward<4>)
+__device__ __forceinline__ void sh4_eval(float x, float y, float z, float out[16]) {
+    float Q[4][5];
+    legendre_derivs<4>(z, Q);
+    float re[4], im[4];
+    re[0] = 1.f; im[0] = 0.f;
+#pragma unroll
+    for (int m = 1; m < 4; ++m) { re[m] = x * re[m - 1] - y * im[m - 1]; im[m] = x * im[m - 1] + y * re[m - 1]; }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        out[l * l + l] = c_shN[l][0] * Q[l][0];
+#pragma unroll
+        for (int m = 1; m <= l; ++m) {
+            const float nq = c_shN[l][m] * Q[l][m];
+            out[l * l + l + m] = nq * re[m];
+            out[l * l + l - m] = nq * im[m];
+        }
     }
 }
 
-// issue one layer: D[128 x N] = A[128 x K] * W^T, K-major SW128 operands
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_addr, uint32_t w_addr, uint32_t N, uint32_t K) {
-    const uint32_t idesc = make_idesc(TILE_M, N, 0, 0);
-    for (uint32_t k = 0; k < K; k += 16) {
-        const uint64_t ad = make_desc(a_addr + k * 2, 16, 1024, LAYOUT_SW128);
-        const uint64_t bd = make_desc(w_addr + k * 2, 16, 1024, LAYOUT_SW128);
-        mma_f16(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+// color-net input row [SH4 | geo(15) | 0] -> 4 x 16-byte chunks of the swizzled tile row `r`
+__device__ __forceinline__ void write_shgeo_row(uint32_t tile_addr, uint32_t r, bool ok, const float* __restrict__ dirs,
+                                                const __half* __restrict__ h_sigma, size_t row) {
+    uint4 c[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (ok) {
+        float sh[16];
+        sh4_eval(__ldg(dirs + row * 3), __ldg(dirs + row * 3 + 1), __ldg(dirs + row * 3 + 2), sh);
+        uint32_t p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) p[i] = pack_h2(sh[2 * i], sh[2 * i + 1]);
+        c[0] = make_uint4(p[0], p[1], p[2], p[3]);
+        c[1] = make_uint4(p[4], p[5], p[6], p[7]);
+        // geo = h[1..15] shifted down by one half; last lane of the row is the zero pad (network_ff.py:67)
+        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16));
+        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16) + 1);
+        const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        uint32_t g[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = (w[i] >> 16) | ((i < 7 ? w[i + 1] : 0u) << 16);
+        c[2] = make_uint4(g[0], g[1], g[2], g[3]);
+        c[3] = make_uint4(g[4], g[5], g[6], g[7]);
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) st_shared_v4(tile_addr + sw128_off(r, k), c[k]);
+}
+
+struct LevelParams { uint32_t off, size, res; float scale; };
+
+// hash-grid features of one sample -> swizzled tile row (+ optional global stash); D=3, C=2, fp16 table, linear interp
+__device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, bool ok, const FieldArgs& fa,
+                                               const LevelParams* __restrict__ lv, size_t row) {
+    float x[3] = {0.5f, 0.5f, 0.5f};
+    bool oob = !ok;
+    if (ok) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            // GridEncoder.forward: (inputs + bound) / (2 * bound); torch divides by a scalar as a multiply by 1/s
+            x[d] = (__ldg(fa.xyz + row * 3 + d) + fa.bound) * fa.inv_2bound;
+            if (x[d] < 0 || x[d] > 1) oob = true;
+        }
+    }
+    const uint32_t nchunk = fa.L >> 2;     // 4 levels (8 halves) per 16-byte chunk
+    for (uint32_t ch = 0; ch < nchunk; ++ch) {
+        uint32_t packed[4] = {0, 0, 0, 0};
+        if (!oob) {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const LevelParams P = lv[ch * 4 + q];
+                float pos[3];
+                uint32_t pg[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    pos[d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
+                    pg[d] = (uint32_t)floorf(pos[d]);
+                    pos[d] -= (float)pg[d];
+                }
+                uint32_t cidx[8];
+                corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
+                const __half2* lvl = reinterpret_cast<const __half2*>(fa.table) + P.off;
+                __half2 val[8];
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i) {
+                    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(lvl + cidx[i]));
+                    val[i] = *reinterpret_cast<const __half2*>(&u);
+                }
+                __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i) {
+                    float w = 1;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) w *= ((i & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+                    acc2(acc, w, val[i]);
+                }
+                packed[q] = *reinterpret_cast<const uint32_t*>(&acc);
+            }
+        }
+        const uint4 v = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        st_shared_v4(tile_addr + sw128_off(r, ch), v);
+        if (ok && fa.feat_out) reinterpret_cast<uint4*>(fa.feat_out + row * (size_t)(fa.L * 2))[ch] = v;
     }
 }
 
 // ================================ forward / inference ==========================================
-template <bool TRAIN, uint32_t ACT>
+template <bool TRAIN, uint32_t ACT, int IN_MODE = IN_PLAIN, int OUT_MODE = OUT_PLAIN>
 __global__ void __launch_bounds__(128)
 k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ weights,
                 __half* __restrict__ forward_buffer, __half* __restrict__ outputs, const uint32_t B,
-                const uint32_t in_dim, const uint32_t num_layers) {
+                const uint32_t in_dim, const uint32_t num_layers, const FieldArgs fa) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ LevelParams lv[32];
+    if constexpr (IN_MODE == IN_GRID) {
+        if (threadIdx.x < fa.L) {
+            const uint32_t l = threadIdx.x;
+            LevelParams P;
+            P.off = (uint32_t)fa.offsets[l];
+            P.size = (uint32_t)fa.offsets[l + 1] - P.off;
+            P.scale = level_scale(l, fa.S, fa.H);
+            P.res = (uint32_t)ceilf(P.scale) + 1;
+            lv[l] = P;
+        }
+    }
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5;
     const uint32_t base = align1024(smem_u32(smem_dyn));
@@ -156,7 +227,9 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
         const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
         const bool row_ok = tid < rows_valid;
         // input tile -> A operand
-        load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+        if constexpr (IN_MODE == IN_GRID) write_grid_row(a_addr, tid, row_ok, fa, lv, row);
+        else if constexpr (IN_MODE == IN_SHGEO) write_shgeo_row(a_addr, tid, row_ok, fa.dirs, fa.h_sigma, row);
+        else load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
 
         for (uint32_t l = 0; l < nmat; ++l) {
             const bool last = (l == nmat - 1);
@@ -205,9 +278,25 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
 #pragma unroll
                 for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                 if (row_ok) {
-                    uint4* o = reinterpret_cast<uint4*>(outputs + row * OUT_PAD);
-                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    if constexpr (OUT_MODE != OUT_RGB) {
+                        uint4* o = reinterpret_cast<uint4*>(outputs + row * OUT_PAD);
+                        o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                        o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    }
+                    if constexpr (OUT_MODE == OUT_SIGMA) {
+                        // trunc_exp forward on the fp16-rounded h[:,0] (the reference casts the half output to float)
+                        const __half2 h01 = *reinterpret_cast<const __half2*>(&p[0]);
+                        if (fa.sigma_out) fa.sigma_out[row] = expf(__low2float(h01));
+                    }
+                    if constexpr (OUT_MODE == OUT_RGB) {
+                        // torch.sigmoid on a half tensor: fp32 math, result rounded to half; handed on as fp32
+                        const __half2 h01 = *reinterpret_cast<const __half2*>(&p[0]);
+                        const __half2 h23 = *reinterpret_cast<const __half2*>(&p[1]);
+                        const float c0 = __half2float(__float2half_rn(1.0f / (1.0f + expf(-__low2float(h01)))));
+                        const float c1 = __half2float(__float2half_rn(1.0f / (1.0f + expf(-__high2float(h01)))));
+                        const float c2 = __half2float(__float2half_rn(1.0f / (1.0f + expf(-__low2float(h23)))));
+                        fa.rgb_out[row * 3] = c0; fa.rgb_out[row * 3 + 1] = c1; fa.rgb_out[row * 3 + 2] = c2;
+                    }
                 }
             }
         }
@@ -361,20 +450,17 @@ k_ffmlp_backward(const __half* __restrict__ grad, const __half* __restrict__ wei
 // Supports num_layers + 1 <= 6 matmuls (NeRF: 3 and 4); wider nets fall back to the two-kernel path.
 static constexpr uint32_t FUSED_MAX_MATMULS = 6;
 
-__device__ __forceinline__ void issue_wgrad(uint32_t acc_tmem, uint32_t p_addr, uint32_t q_addr, uint32_t accumulate) {
-    const uint32_t idesc = make_idesc(64, 64, 1, 1);
-#pragma unroll
-    for (uint32_t k = 0; k < TILE_M / 16; ++k)
-        mma_f16(acc_tmem, make_desc(p_addr + k * 2048, 16384, 1024, LAYOUT_SW128),
-                make_desc(q_addr + k * 2048, 16384, 1024, LAYOUT_SW128), idesc, (accumulate || k > 0) ? 1u : 0u);
-}
-
-template <uint32_t ACT>
+// FIELD_COLOR variant (color net of the NeRF field): dL/dy is formed on the fly from (d_rgb, rgb) through the sigmoid,
+// the input tile for the first-layer weight gradient is re-assembled from (dirs, h_sigma) like in the forward, and the
+// "grad_inputs" epilogue emits dL/d(sigma-net output) [M,16] = [d_sigma * exp(clamp(h0)), d_geo(15)] directly
+// (replaces sigmoid/cat/slice/trunc_exp backward glue, network_ff.py:56-72 + activation.py:13-16).
+template <uint32_t ACT, bool FIELD_COLOR = false>
 __global__ void __launch_bounds__(128)
 k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict__ inputs,
                        const __half* __restrict__ weights, const __half* __restrict__ forward_buffer,
                        __half* __restrict__ backward_buffer, __half* __restrict__ grad_inputs,
-                       float* __restrict__ wgrad_ws, const uint32_t B, const uint32_t in_dim, const uint32_t num_layers) {
+                       float* __restrict__ wgrad_ws, const uint32_t B, const uint32_t in_dim, const uint32_t num_layers,
+                       const FieldArgs fa) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -418,8 +504,27 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
         const bool row_ok = tid < rows_valid;
         // dL/dy -> G1 (K-major A of round 0 and, zero-padded to 64 columns, MN-major operand of the output-layer wgrad)
-        load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128, rows_valid);
-        zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
+        if constexpr (FIELD_COLOR) {
+            // dL/dh = half(d_rgb) * y (1 - y), y = rgb (already fp16-representable); columns 3..63 are zero
+            uint32_t q0 = 0, q1 = 0;
+            if (row_ok) {
+                float dh[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float y = __ldg(fa.rgb + row * 3 + c);
+                    const float g = __half2float(__float2half_rn(__ldg(fa.d_rgb + row * 3 + c)));
+                    dh[c] = g * (y * (1.0f - y));
+                }
+                q0 = pack_h2(dh[0], dh[1]);
+                q1 = pack_h2(dh[2], 0.f);
+            }
+            st_shared_v4(g_addr[1] + sw128_off(tid, 0), make_uint4(q0, q1, 0, 0));
+#pragma unroll
+            for (uint32_t c = 1; c < 8; ++c) st_shared_v4(g_addr[1] + sw128_off(tid, c), make_uint4(0, 0, 0, 0));
+        } else {
+            load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128, rows_valid);
+            zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
+        }
 
         // round r consumes A = (r == 0 ? G1 : G[(r-1)&1]) and produces dPre of hidden layer (num_layers-1-r) in G[r&1],
         // with the matching forward activations H in F[r&1].
@@ -479,6 +584,22 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                         if (bb && row_ok) bb[half_i * 4 + c] = q;
                     }
                 }
+            } else if constexpr (FIELD_COLOR) {
+                // d(color input) columns 16..30 = d geo_feat; column 0 of the sigma-net output gets the trunc_exp gradient
+                uint32_t v[16];
+                tmem_ld16(t_lane + 16, v);
+                tmem_ld_wait();
+                if (row_ok) {
+                    const float h0 = __half2float(__ldg(fa.h_sigma + row * 16));
+                    const float g0 = __ldg(fa.d_sigma + row) * expf(fminf(fmaxf(h0, -15.f), 15.f));
+                    uint32_t p[8];
+                    p[0] = pack_h2(g0, __uint_as_float(v[0]));
+#pragma unroll
+                    for (uint32_t i = 1; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i - 1]), __uint_as_float(v[2 * i]));
+                    uint4* o = reinterpret_cast<uint4*>(fa.dys_out + row * 16);
+                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                }
             } else {
                 __half* gi = grad_inputs + row * in_dim;
                 for (uint32_t c0 = 0; c0 < in_dim; c0 += 16) {
@@ -501,7 +622,11 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden & 1]; X goes to the other F.
         {
             const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
-            load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+            if constexpr (FIELD_COLOR) {
+                write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+            } else {
+                load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+            }
             zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             fence_async_smem();
             fence_before_sync();
@@ -776,7 +901,7 @@ static int launch_forward(const void* inputs, const void* weights, uint32_t B, u
         rc = set_smem(k_ffmlp_forward<TRAIN, A>, smem, who);
         if (rc == NGP_OK)
             k_ffmlp_forward<TRAIN, A><<<grid, 128, smem, st>>>((const __half*)inputs, (const __half*)weights,
-                                                                (__half*)forward_buffer, (__half*)outputs, B, input_dim, num_layers))
+                                                                (__half*)forward_buffer, (__half*)outputs, B, input_dim, num_layers, FieldArgs{}))
     if (rc) return rc;
     return check_launch(who);
 }
@@ -833,7 +958,7 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
             if (rc == NGP_OK)
                 k_ffmlp_backward_fused<A><<<grid, 128, smem, st>>>((const __half*)grad, (const __half*)inputs, (const __half*)weights,
                                                                    (const __half*)forward_buffer, (__half*)backward_buffer, gi,
-                                                                   (float*)workspace, B, input_dim, num_layers))
+                                                                   (float*)workspace, B, input_dim, num_layers, FieldArgs{}))
         if (rc) return rc;
         rc = check_launch("ffmlp_backward");
         if (rc) return rc;
@@ -866,6 +991,95 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
     }
     k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
     return check_launch("ffmlp_backward(finalize)");
+}
+
+// ---- fused NeRF-field entry points (extensions: the reference has no single op for these; they replace
+// GridEncoder -> FFMLP -> trunc_exp and SHEncoder -> cat -> FFMLP -> sigmoid of nerf/network_ff.py:51-74) -------
+extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32_t* offsets, uint32_t L, float S,
+                                       uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
+                                       uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer,
+                                       void* h_out, float* sigma_out, ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    const uint32_t in_dim = 2 * L;
+    int rc = check_cfg("field_sigma_forward", M, in_dim, OUT_PAD, HID, num_layers, ACT_NONE);
+    if (rc) return rc;
+    if (L % 4 != 0 || L > 32) return fail(NGP_EUNSUPPORTED, "field_sigma_forward: L must be a multiple of 4, <= 32");
+    if (train && (!forward_buffer || !feat_out)) return fail(NGP_EINVAL, "field_sigma_forward: training needs forward_buffer and feat_out");
+    FieldArgs fa{};
+    fa.xyz = x01; fa.bound = 0.f; fa.inv_2bound = 1.f; fa.table = (const __half*)table_f16; fa.offsets = offsets; fa.L = L;
+    fa.S = S; fa.H = H; fa.gridtype = gridtype; fa.align_corners = align_corners; fa.feat_out = (__half*)feat_out;
+    fa.sigma_out = sigma_out;
+    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
+    const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 5);
+    cudaStream_t st = as_stream(stream);
+    if (train) {
+        rc = set_smem(k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA>, smem, "field_sigma_forward");
+        if (rc) return rc;
+        k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, (__half*)forward_buffer,
+                                                                                  (__half*)h_out, M, in_dim, num_layers, fa);
+    } else {
+        rc = set_smem(k_ffmlp_forward<false, ACT_RELU, IN_GRID, OUT_SIGMA>, smem, "field_sigma_forward");
+        if (rc) return rc;
+        k_ffmlp_forward<false, ACT_RELU, IN_GRID, OUT_SIGMA><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, nullptr,
+                                                                                   (__half*)h_out, M, in_dim, num_layers, fa);
+    }
+    return check_launch("field_sigma_forward");
+}
+
+extern "C" int ngp_field_color_forward(const float* dirs, const void* h_sigma, const void* weights, uint32_t num_layers,
+                                       uint32_t M, int train, void* forward_buffer, float* rgb_out, ngp_stream_t stream) {
+    if (M == 0) return NGP_OK;
+    int rc = check_cfg("field_color_forward", M, 32, OUT_PAD, HID, num_layers, ACT_NONE);
+    if (rc) return rc;
+    if (train && !forward_buffer) return fail(NGP_EINVAL, "field_color_forward: training needs forward_buffer");
+    FieldArgs fa{};
+    fa.dirs = dirs; fa.h_sigma = (const __half*)h_sigma; fa.rgb_out = rgb_out;
+    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
+    const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 4);
+    cudaStream_t st = as_stream(stream);
+    if (train) {
+        rc = set_smem(k_ffmlp_forward<true, ACT_RELU, IN_SHGEO, OUT_RGB>, smem, "field_color_forward");
+        if (rc) return rc;
+        k_ffmlp_forward<true, ACT_RELU, IN_SHGEO, OUT_RGB><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, (__half*)forward_buffer,
+                                                                                 nullptr, M, 32, num_layers, fa);
+    } else {
+        rc = set_smem(k_ffmlp_forward<false, ACT_RELU, IN_SHGEO, OUT_RGB>, smem, "field_color_forward");
+        if (rc) return rc;
+        k_ffmlp_forward<false, ACT_RELU, IN_SHGEO, OUT_RGB><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, nullptr, nullptr, M, 32,
+                                                                                  num_layers, fa);
+    }
+    return check_launch("field_color_forward");
+}
+
+extern "C" int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* d_sigma, const void* h_sigma,
+                                        const float* dirs, const void* weights, const void* forward_buffer,
+                                        uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
+                                        size_t workspace_bytes, ngp_stream_t stream) {
+    int rc = check_cfg("field_color_backward", M, 32, OUT_PAD, HID, num_layers, ACT_NONE);
+    if (rc) return rc;
+    if (num_layers + 1 > FUSED_MAX_MATMULS) return fail(NGP_EUNSUPPORTED, "field_color_backward: num_layers must be <= 5");
+    const size_t need = ngp_ffmlp_backward_workspace_bytes(M, 32, OUT_PAD, HID, num_layers);
+    if (!workspace || workspace_bytes < need) return fail(NGP_EINVAL, "field_color_backward: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return fail(NGP_ECUDA, "field_color_backward: memset failed");
+    if (M > 0) {
+        FieldArgs fa{};
+        fa.d_rgb = d_rgb; fa.rgb = rgb; fa.d_sigma = d_sigma; fa.h_sigma = (const __half*)h_sigma; fa.dirs = dirs;
+        fa.dys_out = (__half*)dys_out;
+        const uint32_t nslots = 1 + (num_layers - 1) + 1;
+        const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
+        const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 2);
+        rc = set_smem(k_ffmlp_backward_fused<ACT_RELU, true>, smem, "field_color_backward");
+        if (rc) return rc;
+        // grad_inputs is only a non-null flag here (the epilogue writes dys_out instead)
+        k_ffmlp_backward_fused<ACT_RELU, true><<<grid, 128, smem, st>>>(nullptr, nullptr, (const __half*)weights, (const __half*)forward_buffer,
+                                                                        nullptr, (__half*)dys_out, (float*)workspace, M, 32, num_layers, fa);
+        rc = check_launch("field_color_backward");
+        if (rc) return rc;
+    }
+    const uint32_t n_params = (uint32_t)(need / sizeof(float));
+    k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
+    return check_launch("field_color_backward(finalize)");
 }
 
 extern "C" int ngp_ffmlp_allocate_splitk(size_t size) { (void)size; return NGP_OK; }

@@ -40,8 +40,9 @@ class NeRFFieldFF(nn.Module):
     """Field of nerf/network_ff.py:11-89 (hashgrid 16x2 -> FFMLP 32-64-64-16; SH4 (+) 15 geo (+) pad -> FFMLP 32-64-64-64-16)."""
 
     def __init__(self, bound=1, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3, hidden_dim_color=64,
-                 density_scale=1, min_near=0.2, density_thresh=0.01, grid_size=128):
+                 density_scale=1, min_near=0.2, density_thresh=0.01, grid_size=128, fused=False):
         super().__init__()
+        self.fused = fused       # True: evaluate the field through nerf_fused.fused_field (same math, fused kernels)
         self.bound = bound
         self.cascade = 1 + math.ceil(math.log2(bound))
         self.grid_size = grid_size
@@ -64,6 +65,9 @@ class NeRFFieldFF(nn.Module):
         self.local_step = 0
 
     def forward(self, x, d):
+        if self.fused:
+            from nerf_fused import fused_field
+            return fused_field(self.encoder, self.sigma_net, self.color_net, x, d, self.bound)
         x = self.encoder(x, bound=self.bound)
         h = self.sigma_net(x)
         sigma = trunc_exp(h[..., 0])
