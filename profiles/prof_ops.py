@@ -57,3 +57,26 @@ if what in ("grid", "all"):
         nb.call("ngp_grid_encode_backward", g.data_ptr(), x01.data_ptr(), None, od.data_ptr(), ge.data_ptr(), M, 3, 2, 16, S, 16, None, None, 0, 0, 0, 1, 0)
     torch.cuda.synchronize()
     print("grid samples", M)
+
+if what in ("field", "all"):
+    # fused field forward/backward at a steady-state-like size, ray-ordered samples
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import synth_rays
+    import raymarching
+    from nerf_step import NeRFFieldFF
+    import ngp_synth as S
+    m = NeRFFieldFF(bound=1, fused=True).cuda().train()
+    grid, _ = S.box_union_density(128, seed=12)
+    m.density_bitfield.copy_(torch.from_numpy(S.packbits_np(grid.numpy())).cuda())
+    N = 65536
+    ro, rd, bf, _ = synth_rays(N)
+    ro, rd = ro.to(dev), rd.to(dev)
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, m.aabb_train, 0.2)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(ro, rd, 1, m.density_bitfield, 1, 128, nears, fars, None, -1, True, 128, True, 0, 1024)
+    for _ in range(2):
+        m.zero_grad()
+        with torch.autocast("cuda", dtype=torch.float16):
+            s, c = m(xyzs, dirs)
+        (s.sum() * 1e-3 + c.sum()).backward()
+    torch.cuda.synchronize()
+    print("field samples", xyzs.shape[0])

@@ -32,9 +32,9 @@ def test_fused_forward_matches_unfused(M):
         s1, c1 = b(x, d)
     assert s1.dtype == torch.float32 and c1.dtype == torch.float32 and c1.shape == (M, 3)
     # same kernels, same rounding points: sigma within an ulp of exp, rgb within one fp16 ulp of sigmoid
-    assert rel_err(s1.cpu().numpy(), s0.float().cpu().numpy()) < 1e-6
-    assert (c1 - c0.float()).abs().max().item() <= 1e-3
-    assert (c1 != c0.float()).float().mean().item() < 0.01
+    assert rel_err(s1.detach().cpu().numpy(), s0.detach().float().cpu().numpy()) < 1e-6
+    assert (c1.detach() - c0.detach().float()).abs().max().item() <= 1e-3
+    assert (c1.detach() != c0.detach().float()).float().mean().item() < 0.01
 
 
 def test_fused_backward_matches_unfused():
@@ -67,8 +67,10 @@ def test_fused_train_step_runs_and_matches_loss():
     rays_o, rays_d, _, _ = synth_rays(N)
     ro, rd = rays_o.cuda(), rays_d.cuda()
     target = torch.rand(N, 3, generator=gen(5)).cuda()
-    la, _ = train_step(a, ro, rd, target, perturb=False, force_all_rays=True)
-    lb, _ = train_step(b, ro, rd, target, perturb=False, force_all_rays=True)
+    # loss scaling as in real training (GradScaler): without it the table gradients sit in fp16's subnormal range
+    sa = torch.amp.GradScaler("cuda", init_scale=65536.0); sb = torch.amp.GradScaler("cuda", init_scale=65536.0)
+    la, _ = train_step(a, ro, rd, target, None, sa, perturb=False, force_all_rays=True)
+    lb, _ = train_step(b, ro, rd, target, None, sb, perturb=False, force_all_rays=True)
     assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(la.item()))
     ga, gb = a.encoder.embeddings.grad, b.encoder.embeddings.grad
-    assert float((ga - gb).norm() / ga.norm()) < 5e-2
+    assert float((ga - gb).norm() / ga.norm()) < 3e-2

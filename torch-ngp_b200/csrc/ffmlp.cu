@@ -267,7 +267,21 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
                     for (uint32_t c = 0; c < 4; ++c) {
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                         st_shared_v4(a_addr + sw128_off(tid, half_i * 4 + c), q);
-                        if (TRAIN && row_ok) reinterpret_cast<uint4*>(fb)[half_i * 4 + c] = q;
+                    }
+                }
+                if (TRAIN) {
+                    // stash the layer output: the warp re-reads ITS 32 rows from the smem tile and stores 4 full
+                    // 128-byte rows per instruction (thread-per-row stores would touch 32 lines per instruction and
+                    // serialise in the LSU: r1 profile)
+                    __syncwarp();
+                    (void)fb;
+                    const uint32_t lane = tid & 31u;
+                    __half* fbl = forward_buffer + ((size_t)l * B + row0) * HID;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8; ++k) {
+                        const uint32_t rl = warp * 32 + k * 4 + (lane >> 3), ch = lane & 7u;
+                        const uint4 q = ld_shared_v4(a_addr + sw128_off(rl, ch));
+                        if (rl < rows_valid) reinterpret_cast<uint4*>(fbl + (size_t)rl * HID)[ch] = q;
                     }
                 }
             } else {
@@ -533,13 +547,12 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             const uint32_t K = (r == 0) ? OUT_PAD : HID;
             const uint32_t N = to_inputs ? in_dim : HID;
             const uint32_t a_in = (r == 0) ? g_addr[1] : g_addr[(r - 1) & 1u];
-            // prefetch this round's forward activations (ReLU mask + wgrad operand) while the MMAs run
-            uint4 f[8];
-            if (!to_inputs) {
-                const uint4* fwd = reinterpret_cast<const uint4*>(forward_buffer + ((size_t)(num_layers - 1 - r) * B + row) * HID);
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) f[c] = row_ok ? __ldg(fwd + c) : make_uint4(0, 0, 0, 0);
-            }
+            // this round's forward activations (ReLU mask + wgrad operand): coalesced rows -> F[r&1] (free: its last
+            // reader, the wgrad issued in round r-1, completed with that round's commit)
+            // ... fetched with cp.async so the copy overlaps the MMAs of this round
+            if (!to_inputs)
+                load_tile_rowmajor_async(f_addr[r & 1u], forward_buffer + ((size_t)(num_layers - 1 - r) * B + row0) * HID, TILE_M,
+                                         HID, tid, 128, rows_valid);
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
@@ -560,6 +573,10 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             mbar_wait(&bar, phase);
             phase ^= 1u;
             fence_after_sync();
+            if (!to_inputs) {           // uniform branch: the F tile copies of all threads must have landed
+                cp_async_wait_all();
+                __syncthreads();
+            }
 
             if (!to_inputs) {
                 const uint32_t gw = g_addr[r & 1u], fw = f_addr[r & 1u];
@@ -568,8 +585,11 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 for (uint32_t half_i = 0; half_i < 2; ++half_i) {
                     uint32_t v[32];
                     tmem_ld32(t_lane + half_i * 32, v);
+                    uint4 f[4];
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; ++c) f[c] = ld_shared_v4(fw + sw128_off(tid, half_i * 4 + c));
                     tmem_ld_wait();
-                    const __half2* fh = reinterpret_cast<const __half2*>(&f[half_i * 4]);
+                    const __half2* fh = reinterpret_cast<const __half2*>(f);
                     uint32_t p[16];
 #pragma unroll
                     for (uint32_t i = 0; i < 16; ++i) {
@@ -580,7 +600,6 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                     for (uint32_t c = 0; c < 4; ++c) {
                         const uint4 q = make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]);
                         st_shared_v4(gw + sw128_off(tid, half_i * 4 + c), q);
-                        st_shared_v4(fw + sw128_off(tid, half_i * 4 + c), f[half_i * 4 + c]);
                         if (bb && row_ok) bb[half_i * 4 + c] = q;
                     }
                 }

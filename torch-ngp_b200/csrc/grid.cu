@@ -268,6 +268,24 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
 
         uint32_t cidx[1 << D];
         corner_indices<D>(gridtype, align_corners, hashmap_size, resolution, pg, cidx);
+
+        // ---- run structure of this level, shared by all 2^D corners: consecutive lanes in the SAME CELL have
+        // identical corner indices.  (Inactive lanes are isolated so that a run always ends on an active lane.)
+        // NOTE: no short-circuit '&&' here — every lane must execute every shuffle
+        bool same = active;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+            const uint32_t prev_pg = __shfl_up_sync(FULL, pg[d], 1);
+            same = same & (prev_pg == pg[d]);
+        }
+        const int prev_active = __shfl_up_sync(FULL, (int)active, 1);
+        same = same & (prev_active != 0);
+        const bool head = (lane == 0) || !same;
+        const uint32_t heads = __ballot_sync(FULL, head);
+        const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
+        const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
+        const bool issue = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
+
 #pragma unroll
         for (uint32_t idx = 0; idx < (1u << D); ++idx) {
             float w = 1;
@@ -275,30 +293,16 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
             for (uint32_t d = 0; d < D; ++d) w *= ((idx & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
             const uint32_t index = cidx[idx];
 
-            // addends: rounded per sample exactly like the reference when the lane stands alone
+            // addends in fp32; segmented inclusive scan over the run, only as deep as the longest run
             float v[C];
 #pragma unroll
             for (uint32_t c = 0; c < C; ++c) v[c] = w * to_f(g[c]);
-
-            // ---- segmented reduction over runs of equal index ----
-            const uint32_t key = active ? index : (0x80000000u | lane);     // inactive lanes never merge
-            const uint32_t prev = __shfl_up_sync(FULL, key, 1);
-            const bool head = (lane == 0) || (prev != key);
-            const uint32_t heads = __ballot_sync(FULL, head);
-            bool issue = active;
-            if (heads != FULL) {
-                const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
-                // scan only as deep as the longest run in this warp (redux.sync max)
-                const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;
-                for (uint32_t o = 1; o < maxrun; o <<= 1) {
+            for (uint32_t o = 1; o < maxrun; o <<= 1) {
 #pragma unroll
-                    for (uint32_t c = 0; c < C; ++c) {
-                        const float t = __shfl_up_sync(FULL, v[c], o);
-                        if (lane >= my_head + o) v[c] += t;
-                    }
+                for (uint32_t c = 0; c < C; ++c) {
+                    const float t = __shfl_up_sync(FULL, v[c], o);
+                    if (lane >= my_head + o) v[c] += t;
                 }
-                const bool tail = (lane == 31u) || ((heads >> (lane + 1u)) & 1u);
-                issue = active && tail;
             }
             if (issue) {
                 T* dst = lvl + (size_t)index * C;

@@ -58,6 +58,23 @@ __device__ __forceinline__ void load_tile_rowmajor(uint32_t tile_addr, const __h
         st_shared_v4(tile_addr + sw128_off(r, c), v);
     }
 }
+// asynchronous variant: cp.async (LDGSTS) 16-byte copies, zero-filled for rows >= rows_valid; the caller commits the
+// group, later waits (cp_async_wait_all) and barriers before anyone reads the tile.
+__device__ __forceinline__ void load_tile_rowmajor_async(uint32_t tile_addr, const __half* __restrict__ src, uint32_t rows,
+                                                         uint32_t cols, uint32_t tid, uint32_t nthr, uint32_t rows_valid) {
+    const uint32_t cpr = cols >> 3;
+    const uint32_t total = rows * cpr;
+    for (uint32_t g = tid; g < total; g += nthr) {
+        const uint32_t r = g / cpr, c = g - r * cpr;
+        const bool ok = r < rows_valid;
+        const void* gp = reinterpret_cast<const uint4*>(src + (size_t)(ok ? r : 0) * cols) + c;
+        const uint32_t nbytes = ok ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_addr + sw128_off(r, c)), "l"(gp), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // zero-fill chunks [c0, 8) of every row of a tile
 __device__ __forceinline__ void zero_tile_cols(uint32_t tile_addr, uint32_t rows, uint32_t c0, uint32_t tid, uint32_t nthr) {
     const uint32_t cpr = 8 - c0;
