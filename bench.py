@@ -350,7 +350,14 @@ def main():
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"], "unit": "GB/s", "frac": ach_gb / pk["hbm"],
                 "tensor_tflops": ach_tf or None}
-    roof.update({"traffic": None, "peak_source": pk["src"], "avg_launch_ms": per_launch_ms,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(dom)
+        if t:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled per sample to this launch
+            traffic = t["dram_bytes_per_sample"] * dd["units"] / dd["calls"]
+    roof.update({"traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full, per-sample x samples/launch)" if traffic else None,
+                 "peak_source": pk["src"], "avg_launch_ms": per_launch_ms,
                  "share_of_step": dd["ms"] / ms_total, "algorithmic_bytes_per_launch": dd["bytes"] / dd["calls"]})
     breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
                      "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None,
