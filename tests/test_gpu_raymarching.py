@@ -68,6 +68,35 @@ def test_march_rays_train_bitexact_vs_oracle(dt_gamma, perturb):
         np.testing.assert_array_equal(gather_segments(a.cpu().numpy(), rays_h), gather_segments(b, orays))
 
 
+def test_march_multi_cascade_bitexact_vs_oracle():
+    """bound = 2 -> two cascades (mip level selection by position / step size, raymarching.cu:42-54, 368)."""
+    from oracle import oracle as O
+    import _ngp_b200 as nb
+    N = 2048
+    rays_o, rays_d, _, _, noises = _scene(N)
+    rays_o = rays_o * 1.6
+    bits = (torch.rand(2 * 128 ** 3 // 8, generator=gen(9)) < 0.02).to(torch.uint8) * torch.randint(1, 255, (2 * 128 ** 3 // 8,), generator=gen(10), dtype=torch.uint8)
+    aabb = np.array([-2, -2, -2, 2, 2, 2], np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), aabb, 0.2)
+    for dt_gamma in (0.0, 1.0 / 128):
+        M = N * 512
+        ox, od_, odl, orays, ocnt = O.march_rays_train(rays_o.numpy(), rays_d.numpy(), bits.numpy(), 2.0, dt_gamma, 1024, 2, 128, M,
+                                                       nears, fars, noises.numpy())
+        xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+        rays = torch.zeros(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+        ro, rd, bf = rays_o.cuda(), rays_d.cuda(), bits.cuda()
+        nd, fd, nz = torch.from_numpy(nears).cuda(), torch.from_numpy(fars).cuda(), noises.cuda()
+        nb.call("ngp_march_rays_train", ro.data_ptr(), rd.data_ptr(), bf.data_ptr(), 2.0, dt_gamma, 1024, N, 2, 128, M,
+                nd.data_ptr(), fd.data_ptr(), xyzs.data_ptr(), dirs.data_ptr(), deltas.data_ptr(), rays.data_ptr(),
+                counter.data_ptr(), nz.data_ptr())
+        assert counter.cpu().tolist() == ocnt.tolist() and ocnt[0] > 0
+        r = rays.cpu().numpy()
+        np.testing.assert_array_equal(canon_rays(r)[:, [0, 2]], canon_rays(orays)[:, [0, 2]])
+        np.testing.assert_array_equal(gather_segments(xyzs.cpu().numpy(), r), gather_segments(ox, orays))
+        np.testing.assert_array_equal(gather_segments(deltas.cpu().numpy(), r), gather_segments(odl, orays))
+    assert (canon_rays(orays)[:, 2] > 64).any()     # rays longer than the shared-memory sample cache take the fallback pass
+
+
 def test_march_rays_train_overflow_and_wrapper():
     """M smaller than the total: dropped rays keep (id, offset, count) but write nothing; wrapper shape rules."""
     import raymarching

@@ -79,20 +79,32 @@ __device__ __forceinline__ void ray_setup(RayConst& r, const float* __restrict__
 
 // One marching decision at parameter t: returns true if the cell is occupied (a sample is taken
 // at (x,y,z) with step dt); otherwise advances t past the empty cell.  Mirrors :357-399.
+// Strength reductions that keep every result bit-identical (the kernel is ALU-bound: ~130 M of these per step):
+//   * the reference's float->double->float cell index chain, (float)(0.5 * (double)a * (double)H), is one correctly
+//     rounded product of a with the exactly representable constant 0.5*H, i.e. the single FMUL a * (0.5f*H);
+//   * with a single cascade (C == 1) both mip_from_* clamp to level 0: frexp/scalbn/reciprocal drop out;
+//   * with dt_gamma == 0 the step clamp(t*0, dt_min, dt_max) is the constant dt_min (also for t = inf: NaN clamps
+//     to dt_min through fmaxf/fminf), so the empty-space loop is add/compare only.
 __device__ __forceinline__ bool march_probe(const RayConst& r, const uint8_t* __restrict__ grid, float& t,
                                             float& x, float& y, float& z, float& dt) {
     x = clampf(fmaf(t, r.dx, r.ox), -r.bound, r.bound);
     y = clampf(fmaf(t, r.dy, r.oy), -r.bound, r.bound);
     z = clampf(fmaf(t, r.dz, r.oz), -r.bound, r.bound);
-    dt = clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
+    const bool const_dt = (r.dt_gamma == 0.0f);
+    dt = const_dt ? r.dt_min : clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
 
-    const int level = max(mip_from_pos(x, y, z, r.fC), mip_from_dt(dt, r.fH, r.fC));
-    const float mip_bound = fminf(scalbnf(1.0f, level), r.bound);
-    const float mip_rbound = 1.0f / mip_bound;
+    int level = 0;
+    float mip_bound = fminf(1.0f, r.bound), mip_rbound;
+    if (r.fC > 1.0f) {
+        level = max(mip_from_pos(x, y, z, r.fC), mip_from_dt(dt, r.fH, r.fC));
+        mip_bound = fminf(scalbnf(1.0f, level), r.bound);
+    }
+    mip_rbound = 1.0f / mip_bound;
 
-    const int nx = (int)clampf((float)(0.5 * (double)fmaf(x, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
-    const int ny = (int)clampf((float)(0.5 * (double)fmaf(y, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
-    const int nz = (int)clampf((float)(0.5 * (double)fmaf(z, mip_rbound, 1.0f) * (double)r.H), 0.0f, r.Hm1);
+    const float halfH = 0.5f * r.fH;
+    const int nx = (int)clampf(fmaf(x, mip_rbound, 1.0f) * halfH, 0.0f, r.Hm1);
+    const int ny = (int)clampf(fmaf(y, mip_rbound, 1.0f) * halfH, 0.0f, r.Hm1);
+    const int nz = (int)clampf(fmaf(z, mip_rbound, 1.0f) * halfH, 0.0f, r.Hm1);
 
     const uint32_t index = (uint32_t)fmaf((float)level, r.H3, (float)morton_enc(nx, ny, nz));
     const bool occ = __ldg(grid + (index >> 3)) & (1u << (index & 7u));
@@ -102,9 +114,11 @@ __device__ __forceinline__ bool march_probe(const RayConst& r, const uint8_t* __
     const float ty = (fmaf(fmaf(fmaf(0.5f, signf1(r.dy), (float)ny + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -y)) * r.rdy;
     const float tz = (fmaf(fmaf(fmaf(0.5f, signf1(r.dz), (float)nz + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -z)) * r.rdz;
     const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
-    do {
-        t += clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
-    } while (t < tt);
+    if (const_dt) {
+        do { t += r.dt_min; } while (t < tt);
+    } else {
+        do { t += clampf(t * r.dt_gamma, r.dt_min, r.dt_max); } while (t < tt);
+    }
     return false;
 }
 
@@ -182,6 +196,15 @@ __global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thr
 }
 
 // ---- training marcher ------------------------------------------------------------------------
+// The reference marches every ray twice (count, then emit).  Here the first pass records the parameter t of each
+// sample it finds (up to MARCH_K per ray) in shared memory; after the warp-aggregated slot reservation the samples
+// of the whole warp are emitted COOPERATIVELY: lane j takes the warp's j-th sample (owner ray found by a shuffle
+// binary search over the warp's inclusive scan), recomputes position / step size from the cached t with exactly the
+// arithmetic of the marching loop, and writes it — consecutive lanes write consecutive samples (coalesced), no
+// divergent re-march.  Rays with more than MARCH_K samples fall back to the per-lane second pass.
+static constexpr uint32_t MARCH_K = 64;
+static constexpr uint32_t MARCH_PITCH = MARCH_K + 1;   // odd pitch: conflict-free reads of one ray's consecutive samples
+
 __global__ void __launch_bounds__(128)
 k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                    const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
@@ -189,11 +212,16 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
                    const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
                    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
                    const float* __restrict__ noises) {
+    __shared__ float tcache[128 * MARCH_PITCH];
+    constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     const bool active = n < N;
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t wbase = threadIdx.x & ~31u;
+    float* my_cache = tcache + threadIdx.x * MARCH_PITCH;
 
     RayConst r;
+    r.ox = r.oy = r.oz = 0.f; r.dx = r.dy = r.dz = 1.f;
     float far = 0.f, t0 = 0.f;
     uint32_t num_steps = 0;
     if (active) {
@@ -201,56 +229,110 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
         const float near = nears[n];
         far = fars[n];
         t0 = fmaf(clampf(near * dt_gamma, r.dt_min, r.dt_max), noises[n], near);
-        // pass 1: count occupied steps
+        // pass 1: count occupied steps, remember where they were
         float t = t0, x, y, z, dt;
         while (t < far && num_steps < max_steps) {
-            if (march_probe(r, grid, t, x, y, z, dt)) { num_steps++; t += dt; }
+            if (march_probe(r, grid, t, x, y, z, dt)) {
+                if (num_steps < MARCH_K) my_cache[num_steps] = t;
+                num_steps++;
+                t += dt;
+            }
         }
+    } else {
+        // shared (warp-uniform) marching constants are needed by every lane in the cooperative phase
+        const float two_sqrt3 = 2 * 1.7320508075688772f;
+        r.bound = bound; r.dt_gamma = dt_gamma;
+        r.dt_min = two_sqrt3 / (float)max_steps;
+        r.dt_max = two_sqrt3 * (float)(1 << (C - 1)) / (float)H;
     }
 
-    // warp-aggregated slot reservation: inclusive scan of num_steps, ballot-rank of active lanes,
-    // one atomic pair by the last active lane's warp leader.
+    // warp-aggregated slot reservation: inclusive scan of num_steps, ballot-rank of active lanes, one atomic pair
     uint32_t incl = num_steps;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
         if (lane >= (uint32_t)o) incl += v;
     }
-    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t act_mask = __ballot_sync(0xffffffffu, active);
+    const uint32_t warp_total = __shfl_sync(FULL, incl, 31);
+    const uint32_t act_mask = __ballot_sync(FULL, active);
+    if (act_mask == 0) return;
     uint32_t base_pt = 0, base_ray = 0;
     if (lane == 0) {
         base_pt = (uint32_t)atomicAdd(counter, (int)warp_total);
         base_ray = (uint32_t)atomicAdd(counter + 1, (int)__popc(act_mask));
     }
-    base_pt = __shfl_sync(0xffffffffu, base_pt, 0);
-    base_ray = __shfl_sync(0xffffffffu, base_ray, 0);
-    if (!active) return;
+    base_pt = __shfl_sync(FULL, base_pt, 0);
+    base_ray = __shfl_sync(FULL, base_ray, 0);
 
     const uint32_t point_index = base_pt + incl - num_steps;
-    const uint32_t ray_index = base_ray + __popc(act_mask & ((1u << lane) - 1u));
-    rays[ray_index * 3] = (int)n;
-    rays[ray_index * 3 + 1] = (int)point_index;
-    rays[ray_index * 3 + 2] = (int)num_steps;
+    if (active) {
+        const uint32_t ray_index = base_ray + __popc(act_mask & ((1u << lane) - 1u));
+        rays[ray_index * 3] = (int)n;
+        rays[ray_index * 3 + 1] = (int)point_index;
+        rays[ray_index * 3 + 2] = (int)num_steps;
+    }
+    const bool fits = active && num_steps > 0 && point_index + num_steps <= M;
 
-    if (num_steps == 0) return;
-    if (point_index + num_steps > M) return;
+    // ---- cooperative emission of the cached rays ----
+    __syncwarp();
+    const uint32_t cnt = (fits && num_steps <= MARCH_K) ? num_steps : 0u;
+    uint32_t cincl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, cincl, o);
+        if (lane >= (uint32_t)o) cincl += v;
+    }
+    const uint32_t ctotal = __shfl_sync(FULL, cincl, 31);
+    for (uint32_t j0 = 0; j0 < ctotal; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        // owner = first lane whose inclusive count exceeds j
+        uint32_t o = 0;
+#pragma unroll
+        for (uint32_t step = 16; step >= 1; step >>= 1) {
+            const uint32_t v = __shfl_sync(FULL, cincl, o + step - 1);
+            if (v <= j) o += step;
+        }
+        o &= 31u;
+        const uint32_t o_incl = __shfl_sync(FULL, cincl, o), o_cnt = __shfl_sync(FULL, cnt, o);
+        const float ox = __shfl_sync(FULL, r.ox, o), oy = __shfl_sync(FULL, r.oy, o), oz = __shfl_sync(FULL, r.oz, o);
+        const float dx = __shfl_sync(FULL, r.dx, o), dy = __shfl_sync(FULL, r.dy, o), dz = __shfl_sync(FULL, r.dz, o);
+        const float ot0 = __shfl_sync(FULL, t0, o);
+        const uint32_t opt = __shfl_sync(FULL, point_index, o);
+        if (j < ctotal) {
+            const uint32_t sidx = j - (o_incl - o_cnt);
+            const float* oc = tcache + (wbase + o) * MARCH_PITCH;
+            const float t = oc[sidx];
+            float last_t = ot0;
+            if (sidx > 0) { const float tp = oc[sidx - 1]; last_t = tp + clampf(tp * dt_gamma, r.dt_min, r.dt_max); }
+            const float x = clampf(fmaf(t, dx, ox), -bound, bound);
+            const float y = clampf(fmaf(t, dy, oy), -bound, bound);
+            const float z = clampf(fmaf(t, dz, oz), -bound, bound);
+            const float dt = clampf(t * dt_gamma, r.dt_min, r.dt_max);
+            const float t_after = t + dt;
+            const size_t out = (size_t)opt + sidx;
+            xyzs[out * 3] = x; xyzs[out * 3 + 1] = y; xyzs[out * 3 + 2] = z;
+            dirs[out * 3] = dx; dirs[out * 3 + 1] = dy; dirs[out * 3 + 2] = dz;
+            *reinterpret_cast<float2*>(deltas + out * 2) = make_float2(dt, t_after - last_t);
+        }
+    }
 
-    // pass 2: re-march and emit samples
-    float* __restrict__ px = xyzs + (size_t)point_index * 3;
-    float* __restrict__ pd = dirs + (size_t)point_index * 3;
-    float* __restrict__ pl = deltas + (size_t)point_index * 2;
-    float t = t0, last_t = t0, x, y, z, dt;
-    uint32_t step = 0;
-    while (t < far && step < num_steps) {
-        if (march_probe(r, grid, t, x, y, z, dt)) {
-            px[0] = x; px[1] = y; px[2] = z;
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
-            t += dt;
-            *reinterpret_cast<float2*>(pl) = make_float2(dt, t - last_t);
-            last_t = t;
-            px += 3; pd += 3; pl += 2;
-            step++;
+    // ---- fallback: rays with more samples than the cache holds re-march on their own ----
+    if (fits && num_steps > MARCH_K) {
+        float* __restrict__ px = xyzs + (size_t)point_index * 3;
+        float* __restrict__ pd = dirs + (size_t)point_index * 3;
+        float* __restrict__ pl = deltas + (size_t)point_index * 2;
+        float t = t0, last_t = t0, x, y, z, dt;
+        uint32_t step = 0;
+        while (t < far && step < num_steps) {
+            if (march_probe(r, grid, t, x, y, z, dt)) {
+                px[0] = x; px[1] = y; px[2] = z;
+                pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+                t += dt;
+                *reinterpret_cast<float2*>(pl) = make_float2(dt, t - last_t);
+                last_t = t;
+                px += 3; pd += 3; pl += 2;
+                step++;
+            }
         }
     }
 }
