@@ -59,6 +59,7 @@ def test_march_rays_train_bitexact_vs_oracle(dt_gamma, perturb):
     rays_h = rays.cpu().numpy()
     assert counter.cpu().tolist() == ocnt.tolist()
     assert ocnt[0] > N  # the scene is not empty
+    assert (orays[:, 2] > 64).any() and (orays[:, 2] <= 64).any()   # both the smem-cached and the fallback emission paths run
     np.testing.assert_array_equal(canon_rays(rays_h)[:, [0, 2]], canon_rays(orays)[:, [0, 2]])   # ids + counts
     # offsets form a permutation-free tiling of [0, total)
     r = rays_h[np.argsort(rays_h[:, 1], kind="stable")]
@@ -94,7 +95,6 @@ def test_march_multi_cascade_bitexact_vs_oracle():
         np.testing.assert_array_equal(canon_rays(r)[:, [0, 2]], canon_rays(orays)[:, [0, 2]])
         np.testing.assert_array_equal(gather_segments(xyzs.cpu().numpy(), r), gather_segments(ox, orays))
         np.testing.assert_array_equal(gather_segments(deltas.cpu().numpy(), r), gather_segments(odl, orays))
-    assert (canon_rays(orays)[:, 2] > 64).any()     # rays longer than the shared-memory sample cache take the fallback pass
 
 
 def test_march_rays_train_overflow_and_wrapper():

@@ -483,9 +483,8 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
     const uint32_t base = align1024(smem_u32(smem_dyn));
     unsigned char* base_gen = smem_dyn + (base - smem_u32(smem_dyn));
     const uint32_t g_addr[2] = {base, base + A_TILE_BYTES};
-    // F tiles are triple-buffered: round r's activations are fetched (cp.async) one round ahead
-    const uint32_t f_addr[3] = {base + 2 * A_TILE_BYTES, base + 3 * A_TILE_BYTES, base + 4 * A_TILE_BYTES};
-    const uint32_t w_off = 5 * A_TILE_BYTES;
+    const uint32_t f_addr[2] = {base + 2 * A_TILE_BYTES, base + 3 * A_TILE_BYTES};
+    const uint32_t w_off = 4 * A_TILE_BYTES;
     const uint32_t w_addr = base + w_off;
     const uint32_t n_hidden = num_layers - 1;
     const uint32_t nmat = num_layers + 1;
@@ -541,21 +540,18 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
         }
 
-        // forward activations of round 0 (hidden layer num_layers-1) start streaming in now
-        load_tile_rowmajor_async(f_addr[0], forward_buffer + ((size_t)(num_layers - 1) * B + row0) * HID, TILE_M, HID, tid, 128, rows_valid);
-
         // round r consumes A = (r == 0 ? G1 : G[(r-1)&1]) and produces dPre of hidden layer (num_layers-1-r) in G[r&1],
-        // with the matching forward activations H in F[r%3].
+        // with the matching forward activations H in F[r&1].
         for (uint32_t r = 0; r < nrounds; ++r) {
             const bool to_inputs = grad_inputs && (r == nrounds - 1);
             const uint32_t K = (r == 0) ? OUT_PAD : HID;
             const uint32_t N = to_inputs ? in_dim : HID;
             const uint32_t a_in = (r == 0) ? g_addr[1] : g_addr[(r - 1) & 1u];
-            // prefetch the NEXT round's forward activations (ReLU mask + wgrad operand) into F[(r+1)%3]: that buffer's last
-            // reader was the wgrad issued in round r-1 (Q = F[(r-2)%3]), complete since that round's commit
-            const bool prefetch = (r + 1 < 1 + n_hidden);
-            if (prefetch)
-                load_tile_rowmajor_async(f_addr[(r + 1) % 3u], forward_buffer + ((size_t)(num_layers - 2 - r) * B + row0) * HID, TILE_M,
+            // this round's forward activations (ReLU mask + wgrad operand): coalesced rows -> F[r&1] (free: its last
+            // reader, the wgrad issued in round r-1, completed with that round's commit)
+            // ... fetched with cp.async so the copy overlaps the MMAs of this round
+            if (!to_inputs)
+                load_tile_rowmajor_async(f_addr[r & 1u], forward_buffer + ((size_t)(num_layers - 1 - r) * B + row0) * HID, TILE_M,
                                          HID, tid, 128, rows_valid);
             fence_async_smem();
             fence_before_sync();
@@ -567,7 +563,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                     if (r == 1) {          // output layer: P = dY (G1, 16 valid columns), Q = H_{nl-1} (F0)
                         issue_wgrad(acc_addr(nmat - 1), g_addr[1], f_addr[0], first_tile ? 0u : 1u);
                     } else if (r >= 2) {   // hidden matmul (num_layers+1-r): P = dPre (G[(r-2)&1]), Q = H (F[(r-1)&1])
-                        issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) % 3u], first_tile ? 0u : 1u);
+                        issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) & 1u], first_tile ? 0u : 1u);
                     }
                     issue_layer(tmem_base, a_in, w_addr + r * W_SLOT_BYTES, N, K);
                     mma_commit(&bar);
@@ -577,14 +573,13 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             mbar_wait(&bar, phase);
             phase ^= 1u;
             fence_after_sync();
-            if (!to_inputs) {           // uniform branch: this round's F tile (all threads' copies) must have landed
-                if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the group just issued
-                else cp_async_wait_all();
+            if (!to_inputs) {           // uniform branch: the F tile copies of all threads must have landed
+                cp_async_wait_all();
                 __syncthreads();
             }
 
             if (!to_inputs) {
-                const uint32_t gw = g_addr[r & 1u], fw = f_addr[r % 3u];
+                const uint32_t gw = g_addr[r & 1u], fw = f_addr[r & 1u];
                 uint4* bb = backward_buffer ? reinterpret_cast<uint4*>(backward_buffer + ((size_t)r * B + row) * HID) : nullptr;
 #pragma unroll
                 for (uint32_t half_i = 0; half_i < 2; ++half_i) {
@@ -643,9 +638,9 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         }
 
         // tail of the tile: wgrad of the last hidden matmul handled above (if any) and of matmul 0 (P = dPre_0, Q = X).
-        // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden % 3]; X goes to the next F.
+        // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden & 1]; X goes to the other F.
         {
-            const uint32_t xq = f_addr[(n_hidden + 1) % 3u];
+            const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
             if constexpr (FIELD_COLOR) {
                 write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
             } else {
@@ -662,7 +657,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                         // the wgrad that the (absent) input round would have issued: matmul 1 (or the output layer when n_hidden == 0)
                         const uint32_t r = nrounds;   // == 1 + n_hidden
                         if (r == 1) issue_wgrad(acc_addr(nmat - 1), g_addr[1], f_addr[0], first_tile ? 0u : 1u);
-                        else issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) % 3u], first_tile ? 0u : 1u);
+                        else issue_wgrad(acc_addr(num_layers + 1 - r), g_addr[(r - 2) & 1u], f_addr[(r - 1) & 1u], first_tile ? 0u : 1u);
                     }
                     issue_wgrad(acc_addr(0), g_addr[n_hidden & 1u], xq, first_tile ? 0u : 1u);
                     mma_commit(&bar);
@@ -975,7 +970,7 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
     __half* gi = calc_grad_inputs ? (__half*)grad_inputs : nullptr;
     if (B > 0 && nmat <= FUSED_MAX_MATMULS) {
         const uint32_t nslots = 1 + (num_layers - 1) + (calc_grad_inputs ? 1 : 0);
-        const size_t smem = 1024 + 5 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
+        const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
         const uint32_t grid = persistent_grid((B + TILE_M - 1) / TILE_M, 2);
         NGP_DISPATCH_ACT(activation,
             rc = set_smem(k_ffmlp_backward_fused<A>, smem, "ffmlp_backward");
@@ -1034,7 +1029,7 @@ extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, 
     fa.S = S; fa.H = H; fa.gridtype = gridtype; fa.align_corners = align_corners; fa.feat_out = (__half*)feat_out;
     fa.sigma_out = sigma_out;
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
-    const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 6);
+    const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 5);
     cudaStream_t st = as_stream(stream);
     if (train) {
         rc = set_smem(k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA>, smem, "field_sigma_forward");
@@ -1091,7 +1086,7 @@ extern "C" int ngp_field_color_backward(const float* d_rgb, const float* rgb, co
         fa.d_rgb = d_rgb; fa.rgb = rgb; fa.d_sigma = d_sigma; fa.h_sigma = (const __half*)h_sigma; fa.dirs = dirs;
         fa.dys_out = (__half*)dys_out;
         const uint32_t nslots = 1 + (num_layers - 1) + 1;
-        const size_t smem = 1024 + 5 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
+        const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
         const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 2);
         rc = set_smem(k_ffmlp_backward_fused<ACT_RELU, true>, smem, "field_color_backward");
         if (rc) return rc;
