@@ -19,19 +19,18 @@ import _ngp_b200 as _backend
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 _interp_to_id = {'linear': 0, 'smoothstep': 1}
 
-_half_cache = {}  # data_ptr -> (version, half tensor)
-
-
 def _half_table(embeddings):
-    key = embeddings.data_ptr()
+    """fp16 shadow of the table, cached ON the parameter object and invalidated by its autograd version counter
+    (optimizer steps bump it).  Keying by data_ptr would be wrong: freed tables get their address reused."""
     ver = embeddings._version
-    hit = _half_cache.get(key)
+    hit = getattr(embeddings, "_ngp_half_shadow", None)
     if hit is not None and hit[0] == ver and hit[1].shape == embeddings.shape and hit[1].device == embeddings.device:
         return hit[1]
     half = embeddings.detach().to(torch.half)
-    if len(_half_cache) > 16:
-        _half_cache.clear()
-    _half_cache[key] = (ver, half)
+    try:
+        embeddings._ngp_half_shadow = (ver, half)
+    except Exception:
+        pass
     return half
 
 
