@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--torch-optimizer", action="store_true", help="GradScaler + torch fused Adam on fp32 .grad (reference trainer sequence) instead of the fused fp16-sink optimizer kernel")
     ap.add_argument("--unfused", action="store_true", help="evaluate the field module by module (network_ff.py call sequence) instead of the fused field kernels")
     return ap.parse_args()
 
@@ -246,23 +247,36 @@ def main():
     host_in, dev_in = make_inputs(R, rank, world, dev)
     log("inputs ready")
     params = [model.encoder.embeddings, model.sigma_net.weights, model.color_net.weights]
-    bucket = ngp_dp.FlatGradBucket(params)
-    opt = torch.optim.Adam(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, fused=True)
-    scaler = torch.amp.GradScaler("cuda", init_scale=128.0)
+    use_fused_opt = not (args.torch_optimizer or args.unfused)
     stage = [tuple(torch.empty_like(t) for t in dev_in[0])]   # device staging for the e2e H2D copies
+    if use_fused_opt:
+        from ngp_optim import FusedFieldOptimizer
+        fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0)
 
-    def step(ro, rd, tgt):
-        bucket.zero()
-        with torch.autocast("cuda", dtype=torch.float16):
-            out = model.render_train(ro, rd, perturb=True)
-            # sum over local rays / global ray count: averaging the allreduce over ranks is then not needed
-            loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)
-        scaler.scale(loss).backward()
-        if world > 1:
-            bucket.allreduce(average=False)
-        scaler.step(opt)
-        scaler.update()
-        return loss, out
+        def step(ro, rd, tgt):
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = model.render_train(ro, rd, perturb=True)
+                loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)
+            (loss * fopt.scale_tensor()).backward()      # fp16 grads land in the flat sink (no fp32 .grad)
+            fopt.step()                                  # [allreduce fp16 sink] + inf check + Adam + shadow refresh + zero
+            return loss, out
+    else:
+        bucket = ngp_dp.FlatGradBucket(params)
+        opt = torch.optim.Adam(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, fused=True)
+        scaler = torch.amp.GradScaler("cuda", init_scale=128.0)
+
+        def step(ro, rd, tgt):
+            bucket.zero()
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = model.render_train(ro, rd, perturb=True)
+                # sum over local rays / global ray count: averaging the allreduce over ranks is then not needed
+                loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)
+            scaler.scale(loss).backward()
+            if world > 1:
+                bucket.allreduce(average=False)
+            scaler.step(opt)
+            scaler.update()
+            return loss, out
 
     # ---- establish the steady-state sample budget (reference: mean_count after the first epoch) ----
     counts = []
@@ -369,7 +383,7 @@ def main():
             "config": {"workload": "nerf_train_800x800_synthetic_lego_boxes", "rays_per_step": R, "rays_per_rank": n_local,
                        "samples_per_ray_mean": samples_per_step_local / max(1, n_local), "occupancy_fill": fill,
                        "hashgrid": "L=16 F=2 T=2^19 base16 ->2048", "mlp": "FFMLP 32-64-64-16 + 32-64-64-64-16 fp16/fp32-acc",
-                       "optimizer": "GradScaler + fused Adam (in timed region)", "field_path": "module-by-module (network_ff.py sequence)" if args.unfused else "fused field kernels (nerf_fused.fused_field)", "parallelism": f"dp{world} (rays sharded in round-robin blocks of 256, 1 allreduce/step)",
+                       "optimizer": ("fused fp16-sink Adam kernel with device-side loss scaling (in timed region)" if use_fused_opt else "GradScaler + torch fused Adam (in timed region)"), "field_path": "module-by-module (network_ff.py sequence)" if args.unfused else "fused field kernels (nerf_fused.fused_field)", "parallelism": f"dp{world} (rays sharded in round-robin blocks of 256, 1 allreduce/step)",
                        "l2": "inputs_exceed_l2 (per-step activations of several GB; 4 camera frames cycled)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world if world > 1 else h2d, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps},

@@ -163,6 +163,15 @@ int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* 
                              const float* dirs, const void* weights, const void* forward_buffer,
                              uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
                              size_t workspace_bytes, ngp_stream_t stream);
+
+/* ---- fused optimizer step (replaces GradScaler.unscale_/inf-check + torch.optim.Adam +
+ * the per-forward fp32->fp16 table cast + gradient zeroing of nerf/utils.py:866-868, main_nerf.py:132, grid.py:43-44).
+ * `state` = 4 device words {float scale, int growth_tracker, int found_inf, int step}; no host synchronisation. ---- */
+int ngp_optim_check_finite(const void* grads, int dtype, uint64_t n, void* state, ngp_stream_t stream);
+int ngp_optim_adam_step(float* params, float* exp_avg, float* exp_avg_sq, void* grads, int dtype, void* shadow_f16,
+                        uint64_t n, float lr, float beta1, float beta2, float eps, const void* state, int zero_grad,
+                        ngp_stream_t stream);
+int ngp_optim_scaler_update(void* state, float growth, float backoff, int growth_interval, ngp_stream_t stream);
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);

@@ -1,0 +1,71 @@
+"""GPU: fused optimizer step (csrc/optim.cu) against torch.optim.Adam + torch.amp.GradScaler semantics."""
+import numpy as np
+import pytest
+import torch
+
+from util import gen, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_adam_matches_torch_and_skips_on_inf():
+    import _ngp_b200 as nb
+    n = 100003
+    p0 = torch.randn(n, generator=gen(1)).cuda()
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    shadow = torch.empty(n, dtype=torch.half, device="cuda")
+    state = torch.zeros(4, dtype=torch.int32, device="cuda"); state[0:1].view(torch.float32).fill_(1024.0)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    for it in range(5):
+        g = torch.randn(n, generator=gen(10 + it)).cuda() * 0.01
+        inject_inf = (it == 2)
+        g16 = (g * 1024.0 * (0.5 if it > 2 else 1.0)).half()       # after the skipped step the scale is halved
+        if inject_inf:
+            g16[123] = float("inf")
+        else:
+            ref.grad = g16.float() / (1024.0 * (0.5 if it > 2 else 1.0))
+            opt.step()
+        gbuf = g16.clone()
+        nb.call("ngp_optim_check_finite", gbuf.data_ptr(), 1, n, state.data_ptr())
+        nb.call("ngp_optim_adam_step", p.data_ptr(), m.data_ptr(), v.data_ptr(), gbuf.data_ptr(), 1, shadow.data_ptr(), n,
+                1e-2, 0.9, 0.99, 1e-15, state.data_ptr(), 1)
+        nb.call("ngp_optim_scaler_update", state.data_ptr(), 2.0, 0.5, 2000)
+        assert float(gbuf.abs().max()) == 0.0                                  # gradient consumed and zeroed
+        st = state.cpu()
+        assert st[2].item() == 0
+        assert st[3].item() == (it + 1 if it < 2 else it)                       # the inf step was skipped
+        assert st[0:1].view(torch.float32).item() == (1024.0 if it < 2 else 512.0)
+        assert rel_err(p.cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+    assert torch.equal(shadow, p.half())
+
+
+def test_fused_optimizer_trains_the_field():
+    """End to end: fp16 gradient sink + fused Adam reduce the loss like GradScaler + torch Adam do."""
+    from nerf_step import NeRFFieldFF
+    from ngp_optim import FusedFieldOptimizer
+    import ngp_synth as S
+    from util import synth_rays
+    torch.manual_seed(1)
+    model = NeRFFieldFF(bound=1, fused=True).cuda().train()
+    grid, _ = S.box_union_density(128, seed=12)
+    model.density_bitfield.copy_(torch.from_numpy(S.packbits_np(grid.numpy())).cuda())
+    opt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, init_scale=1024.0)
+    N = 4096
+    rays_o, rays_d, _, _ = synth_rays(N)
+    ro, rd = rays_o.cuda(), rays_d.cuda()
+    target = torch.rand(1, 3).expand(N, 3).contiguous().cuda()
+    losses = []
+    for it in range(12):
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model.render_train(ro, rd, perturb=True, force_all_rays=True)
+            loss = torch.nn.functional.mse_loss(out["image"], target)
+        (loss * opt.scale_tensor()).backward()
+        assert model.encoder.embeddings.grad is None            # no fp32 .grad was materialised
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0]
+    assert int(opt.state[3].item()) == 12
+    # the fp16 table shadow the next forward will read is the one the kernel refreshed
+    from gridencoder.grid import _half_table
+    assert torch.equal(_half_table(model.encoder.embeddings), model.encoder.embeddings.detach().half())

@@ -32,6 +32,9 @@ _SIGNATURES = {
     "ngp_field_color_forward": [_vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp],
     "ngp_field_color_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp],
     "ngp_debug_umma": [_vp, _vp, _vp, _i32, _vp],
+    "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
+    "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],
+    "ngp_optim_scaler_update": [_vp, _f32, _f32, _i32, _vp],
     "ngp_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "ngp_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
     "ngp_morton3D": [_vp, _u32, _vp, _vp],

@@ -47,6 +47,8 @@ class _fused_field(Function):
         if training:
             ctx.save_for_backward(x01, dirs, offsets, ws, wc, feat, fb_s, fb_c, h, rgb)
             ctx.cfg = (L, S, int(H), gridtype, int(align_corners), nl_s, nl_c, M, tuple(table.shape))
+            # optional fp16 gradient sinks installed by ngp_optim.FusedFieldOptimizer (bypass fp32 .grad accumulation)
+            ctx.sinks = tuple(getattr(p, "_ngp_grad_sink", None) for p in (embeddings, sigma_w, color_w))
         return sigma, rgb
 
     @staticmethod
@@ -59,8 +61,9 @@ class _fused_field(Function):
         d_rgb = d_rgb.float().contiguous()
         lib = _backend.load()
         # color net (+ sigmoid, cat, trunc_exp gradients) -> dL/d(sigma-net output)
+        sink_t, sink_s, sink_c = ctx.sinks
         dys = torch.empty(M, 16, dtype=torch.half, device=dev)
-        gw_c = torch.empty_like(wc)
+        gw_c = sink_c if sink_c is not None else torch.empty_like(wc)
         nb_c = lib.ngp_ffmlp_backward_workspace_bytes(M, 32, 16, 64, nl_c)
         wk_c = torch.empty(nb_c // 4, dtype=torch.float32, device=dev)
         _backend.call("ngp_field_color_backward", d_rgb.data_ptr(), rgb.data_ptr(), d_sigma.data_ptr(), h.data_ptr(),
@@ -68,16 +71,18 @@ class _fused_field(Function):
                       wk_c.data_ptr(), nb_c)
         # sigma net -> dL/d(features)
         d_feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev)
-        gw_s = torch.empty_like(ws)
+        gw_s = sink_s if sink_s is not None else torch.empty_like(ws)
         nb_s = lib.ngp_ffmlp_backward_workspace_bytes(M, 2 * L, 16, 64, nl_s)
         wk_s = torch.empty(nb_s // 4, dtype=torch.float32, device=dev)
         _backend.call("ngp_ffmlp_backward", dys.data_ptr(), feat.data_ptr(), ws.data_ptr(), fb_s.data_ptr(), M, 2 * L, 16, 64,
                       nl_s, 0, 6, 1, None, d_feat.data_ptr(), gw_s.data_ptr(), wk_s.data_ptr(), nb_s)
         # hash-table scatter-add
-        g_table = torch.zeros(table_shape, dtype=torch.half, device=dev)
+        # (a sink is kept zeroed by the optimizer kernel; otherwise a fresh zero table as in grid.py:77)
+        g_table = sink_t if sink_t is not None else torch.zeros(table_shape, dtype=torch.half, device=dev)
         _backend.call("ngp_grid_encode_backward", d_feat.data_ptr(), x01.data_ptr(), None, offsets.data_ptr(),
                       g_table.data_ptr(), M, 3, 2, L, S, H, None, None, gridtype, align_corners, 0, 1, 0)
-        return None, None, g_table, None, gw_s, gw_c, None
+        return (None, None, None if sink_t is not None else g_table, None, None if sink_s is not None else gw_s,
+                None if sink_c is not None else gw_c, None)
 
 
 def fused_field(encoder, sigma_net, color_net, x, d, bound=1, training=None):
