@@ -59,7 +59,8 @@ def test_march_rays_train_bitexact_vs_oracle(dt_gamma, perturb):
     rays_h = rays.cpu().numpy()
     assert counter.cpu().tolist() == ocnt.tolist()
     assert ocnt[0] > N  # the scene is not empty
-    assert (orays[:, 2] > 64).any() and (orays[:, 2] <= 64).any()   # both the smem-cached and the fallback emission paths run
+    if dt_gamma == 0.0:
+        assert (orays[:, 2] > 64).any() and (orays[:, 2] <= 64).any()   # both the smem-cached and the fallback emission paths run
     np.testing.assert_array_equal(canon_rays(rays_h)[:, [0, 2]], canon_rays(orays)[:, [0, 2]])   # ids + counts
     # offsets form a permutation-free tiling of [0, total)
     r = rays_h[np.argsort(rays_h[:, 1], kind="stable")]
