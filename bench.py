@@ -271,7 +271,13 @@ def main():
         from ngp_optim import FusedFieldOptimizer
         fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0)
 
+        from nerf_step import FusedTrainStep
+        fstep = FusedTrainStep(model, fopt, R, perturb=True)
+
         def step(ro, rd, tgt):
+            if model.mean_count > 0:
+                # steady state: autograd-free step driver (same kernels; MSE gradient in closed form), graph-capturable
+                return fstep(ro, rd, tgt), None
             with torch.autocast("cuda", dtype=torch.float16):
                 out = model.render_train(ro, rd, perturb=True)
                 loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)

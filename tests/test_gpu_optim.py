@@ -69,3 +69,42 @@ def test_fused_optimizer_trains_the_field():
     # the fp16 table shadow the next forward will read is the one the kernel refreshed
     from gridencoder.grid import _half_table
     assert torch.equal(_half_table(model.encoder.embeddings), model.encoder.embeddings.detach().half())
+
+
+def test_fused_train_step_matches_autograd_path():
+    """FusedTrainStep (closed-form MSE gradient, no autograd) == autograd through the fused field + same optimizer."""
+    from nerf_step import NeRFFieldFF, FusedTrainStep
+    from ngp_optim import FusedFieldOptimizer
+    import ngp_synth as S
+    from util import synth_rays
+    N = 8192
+    rays_o, rays_d, _, _ = synth_rays(N)
+    ro, rd = rays_o.cuda(), rays_d.cuda()
+    target = torch.rand(N, 3, generator=gen(5)).cuda()
+    grid, _ = S.box_union_density(128, seed=12)
+    res = []
+    for manual in (False, True):
+        torch.manual_seed(1)
+        model = NeRFFieldFF(bound=1, fused=True).cuda().train()
+        with torch.no_grad():
+            model.encoder.embeddings.uniform_(-0.3, 0.3)
+        model.density_bitfield.copy_(torch.from_numpy(S.packbits_np(grid.numpy())).cuda())
+        opt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, init_scale=1024.0)
+        model.mean_count = 200000
+        if manual:
+            loss = FusedTrainStep(model, opt, N, perturb=False)(ro, rd, target)
+        else:
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = model.render_train(ro, rd, perturb=False)
+                loss = ((out["image"] - target) ** 2).sum() / (3.0 * N)
+            (loss * opt.scale_tensor()).backward()
+            opt.step()
+        res.append((loss.item(), model.encoder.embeddings.detach().clone(), model.color_net.weights.detach().clone(), int(opt.state[3].item())))
+    (la, ea, wa, sa), (lb, eb, wb, sb) = res
+    assert sa == 1 and sb == 1
+    assert abs(la - lb) < 1e-6 * max(1.0, abs(la))
+    # Adam's first step moves every touched parameter by ~lr*sign(g): compare the update directions
+    ua, ub = ea - ea.mean() * 0, eb
+    assert float((ea - eb).abs().max()) <= 2.5e-2                      # at most a sign flip on near-zero gradients (2*lr)
+    assert float(((ea - eb).abs() > 1e-3).float().mean()) < 5e-3       # ...and only for a tiny fraction of entries
+    assert float((wa - wb).abs().max()) <= 2.5e-2

@@ -129,3 +129,52 @@ def train_step(model, rays_o, rays_d, target, optimizer=None, scaler=None, **ren
         if optimizer is not None:
             optimizer.step()
     return loss.detach(), out
+
+
+class FusedTrainStep:
+    """Autograd-free, host-sync-free training step: near/far -> march (steady-state budget) -> fused field
+    -> composite -> MSE -> composite backward -> fused field backward -> fused optimizer, all issued from one thread through
+    the C ABI, so the whole step can be captured in a CUDA graph and replayed.  Same arithmetic as train_step() with
+    NeRFFieldFF(fused=True) + FusedFieldOptimizer: the MSE gradient is formed in closed form instead of by autograd."""
+
+    def __init__(self, model, optimizer, rays_total, bg_color=1.0, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, perturb=True):
+        self.model, self.opt, self.R = model, optimizer, float(rays_total)
+        self.bg, self.T_thresh, self.dt_gamma, self.max_steps, self.perturb = bg_color, T_thresh, dt_gamma, max_steps, perturb
+
+    @torch.no_grad()
+    def __call__(self, rays_o, rays_d, target):
+        import _ngp_b200 as nb
+        from nerf_fused import field_forward, field_backward, field_cfg
+        m = self.model
+        assert m.mean_count > 0, "FusedTrainStep runs the steady-state (mean_count) path; establish the budget first"
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, m.min_near)
+        counter = m.step_counter[0]
+        counter.zero_()
+        xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, m.bound, m.density_bitfield, m.cascade,
+                                                                m.grid_size, nears, fars, counter, m.mean_count, self.perturb,
+                                                                128, False, self.dt_gamma, self.max_steps)
+        cfg = field_cfg(m.encoder, m.sigma_net, m.color_net, m.bound, True)
+        sigma, rgb, stash = field_forward(xyzs, dirs, m.encoder.embeddings, m.encoder.offsets, m.sigma_net.weights,
+                                          m.color_net.weights, cfg)
+        if m.density_scale != 1:
+            sigma = sigma * m.density_scale
+        M, N = sigma.shape[0], rays.shape[0]
+        dev = sigma.device
+        wsum = torch.empty(N, device=dev); depth = torch.empty(N, device=dev); image = torch.empty(N, 3, device=dev)
+        nb.call("ngp_composite_rays_train_forward", sigma.data_ptr(), rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), M, N,
+                float(self.T_thresh), wsum.data_ptr(), depth.data_ptr(), image.data_ptr())
+        pred = image + (1 - wsum).unsqueeze(-1) * self.bg
+        diff = pred - target
+        loss = (diff * diff).sum() / (3.0 * self.R)
+        # d loss / d pred, scaled by the device-resident loss scale
+        g_pred = diff * ((2.0 / (3.0 * self.R)) * self.opt.scale_tensor())
+        g_ws = -(g_pred.sum(-1)) * self.bg
+        g_sigma = torch.zeros(M, device=dev); g_rgb = torch.zeros(M, 3, device=dev)
+        nb.call("ngp_composite_rays_train_backward", g_ws.contiguous().data_ptr(), g_pred.contiguous().data_ptr(), sigma.data_ptr(),
+                rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), wsum.data_ptr(), image.data_ptr(), M, N, float(self.T_thresh),
+                g_sigma.data_ptr(), g_rgb.data_ptr())
+        if m.density_scale != 1:
+            g_sigma = g_sigma * m.density_scale
+        field_backward(stash["tensors"], stash["cfg"], stash["sinks"], g_sigma, g_rgb)
+        self.opt.step()
+        return loss
