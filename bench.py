@@ -390,6 +390,7 @@ def main():
         t1 = sampler.mark()
         clocks = sampler.stop(t0, t1)
         # per-kernel CUDA-event durations need individual launches: the same K steps once more, eagerly
+        run_loop(2, False, eager=True)      # re-warm the eager allocator pool (the graph owns its own)
         ms_eager, launches, rec = timed(args.steps, False, profile=True, eager=True)
         log(f"eager (per-kernel event pass): {ms_eager / args.steps:.2f} ms/step")
     else:
