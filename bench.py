@@ -484,8 +484,15 @@ def main():
                                   "--steps", str(max(3, min(args.steps, 10)))], 300)
     if rank == 0:
         emit(line)
+    # leave without library teardown: destroying a NCCL communicator that is referenced by a live CUDA graph can block
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
