@@ -8,9 +8,9 @@ from util import gen, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def test_adam_matches_torch_and_skips_on_inf():
+@pytest.mark.parametrize("n", [100003, 100000])      # scalar tail path / 128-bit vector path
+def test_adam_matches_torch_and_skips_on_inf(n):
     import _ngp_b200 as nb
-    n = 100003
     p0 = torch.randn(n, generator=gen(1)).cuda()
     p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
     shadow = torch.empty(n, dtype=torch.half, device="cuda")

@@ -61,6 +61,44 @@ __global__ void k_adam_step(float* __restrict__ p, float* __restrict__ m, float*
     }
 }
 
+// 4 parameters per thread per iteration: 128-bit loads/stores of p/m/v, 64-bit of the fp16 grad and shadow
+__global__ void k_adam_step_vec4(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v, uint2* __restrict__ g,
+                                 uint2* __restrict__ shadow, size_t n4, float lr, float beta1, float beta2, float eps,
+                                 const ScalerState* __restrict__ st, int zero_grad) {
+    if (st->found_inf) {
+        if (zero_grad)
+            for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) g[i] = make_uint2(0, 0);
+        return;
+    }
+    const float inv_scale = 1.0f / st->scale;
+    const int step = st->step + 1;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    const float step_size = lr / bc1;
+    const float rsqrt_bc2 = rsqrtf(bc2);
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uint2 gr = g[i];
+        const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&gr.x));
+        const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&gr.y));
+        const float gi[4] = {g01.x * inv_scale, g01.y * inv_scale, g23.x * inv_scale, g23.y * inv_scale};
+        float4 pp = p[i], mm = m[i], vv = v[i];
+        float* pf = reinterpret_cast<float*>(&pp); float* mf = reinterpret_cast<float*>(&mm); float* vf = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mf[k] = fmaf(beta1, mf[k], omb1 * gi[k]);
+            vf[k] = fmaf(beta2, vf[k], omb2 * gi[k] * gi[k]);
+            pf[k] = pf[k] - step_size * (mf[k] / (sqrtf(vf[k]) * rsqrt_bc2 + eps));
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        if (shadow) {
+            const __half2 s01 = __floats2half2_rn(pf[0], pf[1]), s23 = __floats2half2_rn(pf[2], pf[3]);
+            shadow[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&s01), *reinterpret_cast<const uint32_t*>(&s23));
+        }
+        if (zero_grad) g[i] = make_uint2(0, 0);
+    }
+}
+
 // GradScaler.update(): backoff on inf, growth after `growth_interval` clean steps; advances the step count
 __global__ void k_scaler_update(ScalerState* st, float growth, float backoff, int growth_interval) {
     if (st->found_inf) {
@@ -93,6 +131,16 @@ extern "C" int ngp_optim_adam_step(float* params, float* exp_avg, float* exp_avg
     if (n == 0) return NGP_OK;
     const uint32_t blocks = (uint32_t)((n + 256 * 4 - 1) / (256 * 4));
     const uint32_t grid = blocks < (uint32_t)sm_count() * 8 ? (blocks ? blocks : 1) : (uint32_t)sm_count() * 8;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(grads) & 7) == 0 && (reinterpret_cast<uintptr_t>(shadow_f16) & 7) == 0;
+    if (dtype == NGP_F16 && aligned && n % 4 == 0) {
+        const size_t n4 = n / 4;
+        const uint32_t b4 = (uint32_t)((n4 + 255) / 256);
+        const uint32_t g4 = b4 < (uint32_t)sm_count() * 16 ? (b4 ? b4 : 1) : (uint32_t)sm_count() * 16;
+        k_adam_step_vec4<<<g4, 256, 0, as_stream(stream)>>>((float4*)params, (float4*)exp_avg, (float4*)exp_avg_sq, (uint2*)grads,
+                                                            (uint2*)shadow_f16, n4, lr, beta1, beta2, eps, (const ScalerState*)state, zero_grad);
+        return check_launch("optim_adam_step");
+    }
     if (dtype == NGP_F16)
         k_adam_step<__half><<<grid, 256, 0, as_stream(stream)>>>(params, exp_avg, exp_avg_sq, (__half*)grads, (__half*)shadow_f16, n, lr,
                                                                  beta1, beta2, eps, (const ScalerState*)state, zero_grad);
