@@ -134,33 +134,36 @@ __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, b
     for (uint32_t ch = 0; ch < nchunk; ++ch) {
         uint32_t packed[4] = {0, 0, 0, 0};
         if (!oob) {
+            // phase 1: addresses of all 4 x 8 corners, then all 32 gathers back to back (memory-level parallelism: this
+            // thread is the only one working on its sample, so the loads must overlap each other)
+            float pos[4][3];
+            uint32_t vals[4][8];
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
                 const LevelParams P = lv[ch * 4 + q];
-                float pos[3];
                 uint32_t pg[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    pos[d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
-                    pg[d] = (uint32_t)floorf(pos[d]);
-                    pos[d] -= (float)pg[d];
+                    pos[q][d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
+                    pg[d] = (uint32_t)floorf(pos[q][d]);
+                    pos[q][d] -= (float)pg[d];
                 }
                 uint32_t cidx[8];
                 corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
-                const __half2* lvl = reinterpret_cast<const __half2*>(fa.table) + P.off;
-                __half2 val[8];
+                const uint32_t* lvl = reinterpret_cast<const uint32_t*>(fa.table) + P.off;
 #pragma unroll
-                for (uint32_t i = 0; i < 8; ++i) {
-                    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(lvl + cidx[i]));
-                    val[i] = *reinterpret_cast<const __half2*>(&u);
-                }
+                for (uint32_t i = 0; i < 8; ++i) vals[q][i] = __ldg(lvl + cidx[i]);
+            }
+            // phase 2: blend in the reference's corner order
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
                 __half2 acc = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
                 for (uint32_t i = 0; i < 8; ++i) {
                     float w = 1;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) w *= ((i & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
-                    acc2(acc, w, val[i]);
+                    for (int d = 0; d < 3; ++d) w *= ((i & (1u << d)) == 0) ? (1 - pos[q][d]) : pos[q][d];
+                    acc2(acc, w, *reinterpret_cast<const __half2*>(&vals[q][i]));
                 }
                 packed[q] = *reinterpret_cast<const uint32_t*>(&acc);
             }
