@@ -190,7 +190,7 @@ def test_inference_march_and_composite_vs_oracle():
 
 def test_vs_reference_extension():
     """Identical inputs through the reference's own raymarching kernels: counts / positions bit-exact,
-    compositor outputs bit-exact (same __expf), gradients bit-exact."""
+    compositor outputs and gradients equal up to fp32 re-association (same __expf, warp-scan summation order)."""
     from oracle import ref_driver as R
     if not R.available("raymarching"):
         pytest.skip("oracle/_ref/raymarching not built")
@@ -220,14 +220,15 @@ def test_vs_reference_extension():
     sig = (torch.rand(M, generator=gen(40)) * 30).cuda(); rgb = torch.rand(M, 3, generator=gen(41)).cuda()
     rws, rdp, rim = R.composite_rays_train_forward(sig, rgb, deltas, rays, 1e-4)
     ws, dp, im = raymarching.composite_rays_train(sig, rgb, deltas, rays, 1e-4)
-    assert rel_err(ws.cpu().numpy(), rws.cpu().numpy()) < 1e-6 and rel_err(im.cpu().numpy(), rim.cpu().numpy()) < 1e-6
-    assert rel_err(dp.cpu().numpy(), rdp.cpu().numpy()) < 1e-6
+    # the compositor evaluates the per-ray recurrence with warp prefix scans: same terms, re-associated fp32 sums
+    assert rel_err(ws.cpu().numpy(), rws.cpu().numpy()) < 1e-5 and rel_err(im.cpu().numpy(), rim.cpu().numpy()) < 1e-5
+    assert rel_err(dp.cpu().numpy(), rdp.cpu().numpy()) < 1e-5
     gws = torch.randn(N, device="cuda"); gim = torch.randn(N, 3, device="cuda")
     rgs, rgc = R.composite_rays_train_backward(gws, gim, sig, rgb, deltas, rays, rws, rim, 1e-4)
     gs = torch.zeros_like(sig); gc = torch.zeros_like(rgb)
     nb.call("ngp_composite_rays_train_backward", gws.data_ptr(), gim.data_ptr(), sig.data_ptr(), rgb.data_ptr(),
             deltas.data_ptr(), rays.data_ptr(), rws.data_ptr(), rim.data_ptr(), M, N, 1e-4, gs.data_ptr(), gc.data_ptr())
-    assert rel_err(gs.cpu().numpy(), rgs.cpu().numpy()) < 1e-5 and rel_err(gc.cpu().numpy(), rgc.cpu().numpy()) < 1e-6
+    assert rel_err(gs.cpu().numpy(), rgs.cpu().numpy()) < 1e-4 and rel_err(gc.cpu().numpy(), rgc.cpu().numpy()) < 1e-5
     # inference pair
     alive = torch.arange(N, dtype=torch.int32, device="cuda"); rt = rn.clone(); nz0 = torch.zeros(N, device="cuda")
     rx, rdd, rl = R.march_rays(N, 2, alive, rt, ro, rd, 1.0, bf, 1, 128, rn, rf, nz0, 128)

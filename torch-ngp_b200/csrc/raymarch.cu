@@ -338,38 +338,83 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
 }
 
 // ---- training compositor ---------------------------------------------------------------------
+// The reference walks each ray's samples sequentially in one thread (one dependent load + exp per step; a 200-sample
+// ray is a ~200-deep latency chain, and neighbouring threads read segments that are far apart).  Here a warp owns 32
+// rays and processes them one after another COOPERATIVELY: the 32 lanes load 32 consecutive samples of the current ray
+// (coalesced), evaluate alpha in parallel, and obtain the running transmittance / colour / depth with warp prefix
+// scans (product scan for T, sum scans for t and the accumulated colour).  Early termination (T < T_thresh after a
+// sample, that sample included) is found with a ballot.  Results equal the sequential recurrence up to fp32
+// re-association inside the scans (tests: 1e-5 of the output scale).
+__device__ __forceinline__ float warp_incl_prod(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v *= t; }
+    return v;
+}
+__device__ __forceinline__ float warp_incl_sum(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += t; }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __global__ void __launch_bounds__(128)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                       const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M, uint32_t N,
                       float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth,
                       float* __restrict__ image) {
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
-    if (n >= N) return;
-    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
-    if (num_steps == 0 || offset + num_steps > M) {
-        weights_sum[index] = 0; depth[index] = 0;
-        image[index * 3] = 0; image[index * 3 + 1] = 0; image[index * 3 + 2] = 0;
-        return;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x);          // this lane's row of the rays table
+    uint32_t my_index = 0, my_offset = 0, my_count = 0;
+    if (n < N) { my_index = rays[n * 3]; my_offset = rays[n * 3 + 1]; my_count = rays[n * 3 + 2]; }
+    const uint32_t nvalid = __popc(__ballot_sync(FULL, n < N));
+    float o_ws = 0, o_d = 0, o_r = 0, o_g = 0, o_b = 0;                  // results of the ray owned by this lane
+    for (uint32_t k = 0; k < nvalid; ++k) {
+        const uint32_t offset = __shfl_sync(FULL, my_offset, k), cnt = __shfl_sync(FULL, my_count, k);
+        if (cnt == 0 || offset + cnt > M) continue;                      // empty / dropped ray: outputs stay 0
+        const float* __restrict__ sg = sigmas + offset;
+        const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+        const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+        float T = 1.0f, t_acc = 0.f;
+        float pr = 0, pg = 0, pb = 0, pws = 0, pd = 0;                   // per-lane partial sums
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < cnt;
+            float alpha = 0.f, d1 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (valid) {
+                const float2 dd = __ldg(dl + i);
+                alpha = 1.0f - __expf(-__ldg(sg + i) * dd.x);
+                d1 = dd.y;
+                c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
+            }
+            const float p_incl = warp_incl_prod(1.0f - alpha, lane);
+            float p_excl = __shfl_up_sync(FULL, p_incl, 1);
+            if (lane == 0) p_excl = 1.0f;
+            const float t_i = t_acc + warp_incl_sum(d1, lane);
+            const float T_after = T * p_incl;
+            const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
+            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;       // last lane that still contributes
+            if (valid && lane <= last) {
+                const float w = alpha * (T * p_excl);
+                pr = fmaf(w, c0, pr); pg = fmaf(w, c1, pg); pb = fmaf(w, c2, pb);
+                pws += w;
+                pd = fmaf(w, t_i, pd);
+            }
+            if (term) break;
+            T = T * __shfl_sync(FULL, p_incl, 31);
+            t_acc = __shfl_sync(FULL, t_i, 31);
+        }
+        const float r = warp_sum(pr), g = warp_sum(pg), b = warp_sum(pb), ws = warp_sum(pws), d = warp_sum(pd);
+        if (lane == k) { o_r = r; o_g = g; o_b = b; o_ws = ws; o_d = d; }
     }
-    const float* __restrict__ sg = sigmas + offset;
-    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
-    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
-    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0, t = 0, d = 0;
-    for (uint32_t step = 0; step < num_steps; ++step) {
-        const float2 dd = __ldg(dl + step);
-        const float alpha = 1.0f - __expf(-__ldg(sg + step) * dd.x);
-        const float weight = alpha * T;
-        r = fmaf(weight, __ldg(cl + step * 3), r);
-        g = fmaf(weight, __ldg(cl + step * 3 + 1), g);
-        b = fmaf(weight, __ldg(cl + step * 3 + 2), b);
-        t += dd.y;
-        d = fmaf(weight, t, d);
-        ws += weight;
-        T *= 1.0f - alpha;
-        if (T < T_thresh) break;
+    if (n < N) {
+        weights_sum[my_index] = o_ws; depth[my_index] = o_d;
+        image[my_index * 3] = o_r; image[my_index * 3 + 1] = o_g; image[my_index * 3 + 2] = o_b;
     }
-    weights_sum[index] = ws; depth[index] = d;
-    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
 }
 
 __global__ void __launch_bounds__(128)
@@ -378,36 +423,54 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
                       const float* __restrict__ deltas, const int* __restrict__ rays,
                       const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M,
                       uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
-    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
-    if (n >= N) return;
-    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], num_steps = rays[n * 3 + 2];
-    if (num_steps == 0 || offset + num_steps > M) return;
-    const float gws = grad_weights_sum[index];
-    const float gr = grad_image[index * 3], gg = grad_image[index * 3 + 1], gb = grad_image[index * 3 + 2];
-    const float r_final = image[index * 3], g_final = image[index * 3 + 1], b_final = image[index * 3 + 2];
-    const float ws_final = weights_sum[index];
-    const float* __restrict__ sg = sigmas + offset;
-    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
-    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
-    float* __restrict__ gs = grad_sigmas + offset;
-    float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
-    float T = 1.0f, r = 0, g = 0, b = 0, ws = 0;
-    for (uint32_t step = 0; step < num_steps; ++step) {
-        const float d0 = __ldg(dl + step).x;
-        const float c0 = __ldg(cl + step * 3), c1 = __ldg(cl + step * 3 + 1), c2 = __ldg(cl + step * 3 + 2);
-        const float alpha = 1.0f - __expf(-__ldg(sg + step) * d0);
-        const float weight = alpha * T;
-        r = fmaf(weight, c0, r);
-        g = fmaf(weight, c1, g);
-        b = fmaf(weight, c2, b);
-        ws += weight;
-        T *= 1.0f - alpha;
-        gc[step * 3] = gr * weight;
-        gc[step * 3 + 1] = gg * weight;
-        gc[step * 3 + 2] = gb * weight;
-        gs[step] = d0 * (gr * (T * c0 - (r_final - r)) + gg * (T * c1 - (g_final - g)) +
-                         gb * (T * c2 - (b_final - b)) + gws * (1 - ws_final));
-        if (T < T_thresh) break;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x);
+    uint32_t my_index = 0, my_offset = 0, my_count = 0;
+    if (n < N) { my_index = rays[n * 3]; my_offset = rays[n * 3 + 1]; my_count = rays[n * 3 + 2]; }
+    const uint32_t nvalid = __popc(__ballot_sync(FULL, n < N));
+    for (uint32_t k = 0; k < nvalid; ++k) {
+        const uint32_t index = __shfl_sync(FULL, my_index, k), offset = __shfl_sync(FULL, my_offset, k), cnt = __shfl_sync(FULL, my_count, k);
+        if (cnt == 0 || offset + cnt > M) continue;
+        const float gws = __ldg(grad_weights_sum + index);
+        const float gr = __ldg(grad_image + index * 3), gg = __ldg(grad_image + index * 3 + 1), gb = __ldg(grad_image + index * 3 + 2);
+        const float r_final = __ldg(image + index * 3), g_final = __ldg(image + index * 3 + 1), b_final = __ldg(image + index * 3 + 2);
+        const float ws_term = gws * (1 - __ldg(weights_sum + index));
+        const float* __restrict__ sg = sigmas + offset;
+        const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+        const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+        float* __restrict__ gs = grad_sigmas + offset;
+        float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
+        float T = 1.0f, r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < cnt;
+            float alpha = 0.f, d0 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (valid) {
+                d0 = __ldg(dl + i).x;
+                alpha = 1.0f - __expf(-__ldg(sg + i) * d0);
+                c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
+            }
+            const float p_incl = warp_incl_prod(1.0f - alpha, lane);
+            float p_excl = __shfl_up_sync(FULL, p_incl, 1);
+            if (lane == 0) p_excl = 1.0f;
+            const float w = alpha * (T * p_excl);
+            const float T_after = T * p_incl;
+            // colour accumulated up to and including sample i
+            const float r_i = r_acc + warp_incl_sum(w * c0, lane);
+            const float g_i = g_acc + warp_incl_sum(w * c1, lane);
+            const float b_i = b_acc + warp_incl_sum(w * c2, lane);
+            const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
+            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;
+            if (valid && lane <= last) {
+                gc[i * 3] = gr * w; gc[i * 3 + 1] = gg * w; gc[i * 3 + 2] = gb * w;
+                gs[i] = d0 * (gr * (T_after * c0 - (r_final - r_i)) + gg * (T_after * c1 - (g_final - g_i)) +
+                              gb * (T_after * c2 - (b_final - b_i)) + ws_term);
+            }
+            if (term) break;
+            T = T * __shfl_sync(FULL, p_incl, 31);
+            r_acc = __shfl_sync(FULL, r_i, 31); g_acc = __shfl_sync(FULL, g_i, 31); b_acc = __shfl_sync(FULL, b_i, 31);
+        }
     }
 }
 
