@@ -339,8 +339,9 @@ k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ r
 
 // ---- training compositor ---------------------------------------------------------------------
 // The reference walks each ray's samples sequentially in one thread (one dependent load + exp per step; a 200-sample
-// ray is a ~200-deep latency chain, and neighbouring threads read segments that are far apart).  Here a warp owns 32
-// rays and processes them one after another COOPERATIVELY: the 32 lanes load 32 consecutive samples of the current ray
+// ray is a ~200-deep latency chain, and neighbouring threads read segments that are far apart).  Here ONE WARP OWNS ONE
+// RAY (empty rays retire immediately; a first version gave each warp 32 consecutive rays, which serialised the
+// clustered non-empty rays of an image region in the same warp): the 32 lanes load 32 consecutive samples of the ray
 // (coalesced), evaluate alpha in parallel, and obtain the running transmittance / colour / depth with warp prefix
 // scans (product scan for T, sum scans for t and the accumulated colour).  Early termination (T < T_thresh after a
 // sample, that sample included) is found with a ballot.  Results equal the sequential recurrence up to fp32
@@ -368,14 +369,11 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
                       float* __restrict__ image) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x);          // this lane's row of the rays table
-    uint32_t my_index = 0, my_offset = 0, my_count = 0;
-    if (n < N) { my_index = rays[n * 3]; my_offset = rays[n * 3 + 1]; my_count = rays[n * 3 + 2]; }
-    const uint32_t nvalid = __popc(__ballot_sync(FULL, n < N));
-    float o_ws = 0, o_d = 0, o_r = 0, o_g = 0, o_b = 0;                  // results of the ray owned by this lane
-    for (uint32_t k = 0; k < nvalid; ++k) {
-        const uint32_t offset = __shfl_sync(FULL, my_offset, k), cnt = __shfl_sync(FULL, my_count, k);
-        if (cnt == 0 || offset + cnt > M) continue;                      // empty / dropped ray: outputs stay 0
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per row of the rays table
+    if (n >= N) return;                                                   // warp-uniform
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], cnt = rays[n * 3 + 2];
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (cnt != 0 && offset + cnt <= M) {                                  // empty / dropped ray: outputs stay 0
         const float* __restrict__ sg = sigmas + offset;
         const float* __restrict__ cl = rgbs + (size_t)offset * 3;
         const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
@@ -408,12 +406,11 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
             T = T * __shfl_sync(FULL, p_incl, 31);
             t_acc = __shfl_sync(FULL, t_i, 31);
         }
-        const float r = warp_sum(pr), g = warp_sum(pg), b = warp_sum(pb), ws = warp_sum(pws), d = warp_sum(pd);
-        if (lane == k) { o_r = r; o_g = g; o_b = b; o_ws = ws; o_d = d; }
+        r = warp_sum(pr); g = warp_sum(pg); b = warp_sum(pb); ws = warp_sum(pws); d = warp_sum(pd);
     }
-    if (n < N) {
-        weights_sum[my_index] = o_ws; depth[my_index] = o_d;
-        image[my_index * 3] = o_r; image[my_index * 3 + 1] = o_g; image[my_index * 3 + 2] = o_b;
+    if (lane == 0) {
+        weights_sum[index] = ws; depth[index] = d;
+        image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
     }
 }
 
@@ -425,52 +422,48 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
                       uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x);
-    uint32_t my_index = 0, my_offset = 0, my_count = 0;
-    if (n < N) { my_index = rays[n * 3]; my_offset = rays[n * 3 + 1]; my_count = rays[n * 3 + 2]; }
-    const uint32_t nvalid = __popc(__ballot_sync(FULL, n < N));
-    for (uint32_t k = 0; k < nvalid; ++k) {
-        const uint32_t index = __shfl_sync(FULL, my_index, k), offset = __shfl_sync(FULL, my_offset, k), cnt = __shfl_sync(FULL, my_count, k);
-        if (cnt == 0 || offset + cnt > M) continue;
-        const float gws = __ldg(grad_weights_sum + index);
-        const float gr = __ldg(grad_image + index * 3), gg = __ldg(grad_image + index * 3 + 1), gb = __ldg(grad_image + index * 3 + 2);
-        const float r_final = __ldg(image + index * 3), g_final = __ldg(image + index * 3 + 1), b_final = __ldg(image + index * 3 + 2);
-        const float ws_term = gws * (1 - __ldg(weights_sum + index));
-        const float* __restrict__ sg = sigmas + offset;
-        const float* __restrict__ cl = rgbs + (size_t)offset * 3;
-        const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
-        float* __restrict__ gs = grad_sigmas + offset;
-        float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
-        float T = 1.0f, r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
-        for (uint32_t base = 0; base < cnt; base += 32) {
-            const uint32_t i = base + lane;
-            const bool valid = i < cnt;
-            float alpha = 0.f, d0 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-            if (valid) {
-                d0 = __ldg(dl + i).x;
-                alpha = 1.0f - __expf(-__ldg(sg + i) * d0);
-                c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
-            }
-            const float p_incl = warp_incl_prod(1.0f - alpha, lane);
-            float p_excl = __shfl_up_sync(FULL, p_incl, 1);
-            if (lane == 0) p_excl = 1.0f;
-            const float w = alpha * (T * p_excl);
-            const float T_after = T * p_incl;
-            // colour accumulated up to and including sample i
-            const float r_i = r_acc + warp_incl_sum(w * c0, lane);
-            const float g_i = g_acc + warp_incl_sum(w * c1, lane);
-            const float b_i = b_acc + warp_incl_sum(w * c2, lane);
-            const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
-            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;
-            if (valid && lane <= last) {
-                gc[i * 3] = gr * w; gc[i * 3 + 1] = gg * w; gc[i * 3 + 2] = gb * w;
-                gs[i] = d0 * (gr * (T_after * c0 - (r_final - r_i)) + gg * (T_after * c1 - (g_final - g_i)) +
-                              gb * (T_after * c2 - (b_final - b_i)) + ws_term);
-            }
-            if (term) break;
-            T = T * __shfl_sync(FULL, p_incl, 31);
-            r_acc = __shfl_sync(FULL, r_i, 31); g_acc = __shfl_sync(FULL, g_i, 31); b_acc = __shfl_sync(FULL, b_i, 31);
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per ray
+    if (n >= N) return;
+    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], cnt = rays[n * 3 + 2];
+    if (cnt == 0 || offset + cnt > M) return;
+    const float gws = __ldg(grad_weights_sum + index);
+    const float gr = __ldg(grad_image + index * 3), gg = __ldg(grad_image + index * 3 + 1), gb = __ldg(grad_image + index * 3 + 2);
+    const float r_final = __ldg(image + index * 3), g_final = __ldg(image + index * 3 + 1), b_final = __ldg(image + index * 3 + 2);
+    const float ws_term = gws * (1 - __ldg(weights_sum + index));
+    const float* __restrict__ sg = sigmas + offset;
+    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+    float* __restrict__ gs = grad_sigmas + offset;
+    float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
+    float T = 1.0f, r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
+    for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < cnt;
+        float alpha = 0.f, d0 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (valid) {
+            d0 = __ldg(dl + i).x;
+            alpha = 1.0f - __expf(-__ldg(sg + i) * d0);
+            c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
         }
+        const float p_incl = warp_incl_prod(1.0f - alpha, lane);
+        float p_excl = __shfl_up_sync(FULL, p_incl, 1);
+        if (lane == 0) p_excl = 1.0f;
+        const float w = alpha * (T * p_excl);
+        const float T_after = T * p_incl;
+        // colour accumulated up to and including sample i
+        const float r_i = r_acc + warp_incl_sum(w * c0, lane);
+        const float g_i = g_acc + warp_incl_sum(w * c1, lane);
+        const float b_i = b_acc + warp_incl_sum(w * c2, lane);
+        const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
+        const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;
+        if (valid && lane <= last) {
+            gc[i * 3] = gr * w; gc[i * 3 + 1] = gg * w; gc[i * 3 + 2] = gb * w;
+            gs[i] = d0 * (gr * (T_after * c0 - (r_final - r_i)) + gg * (T_after * c1 - (g_final - g_i)) +
+                          gb * (T_after * c2 - (b_final - b_i)) + ws_term);
+        }
+        if (term) break;
+        T = T * __shfl_sync(FULL, p_incl, 31);
+        r_acc = __shfl_sync(FULL, r_i, 31); g_acc = __shfl_sync(FULL, g_i, 31); b_acc = __shfl_sync(FULL, b_i, 31);
     }
 }
 
@@ -588,7 +581,8 @@ extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float
                                                 const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
                                                 float* weights_sum, float* depth, float* image,
                                                 ngp_stream_t stream) {
-    NGP_LAUNCH_1D(k_composite_train_fwd, N, 128, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
+    if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_forward: too many rays");
+    NGP_LAUNCH_1D(k_composite_train_fwd, N * 32, 128, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
                   T_thresh, weights_sum, depth, image);
 }
 extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
@@ -596,7 +590,8 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, 
                                                  const int32_t* rays, const float* weights_sum, const float* image,
                                                  uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
                                                  float* grad_rgbs, ngp_stream_t stream) {
-    NGP_LAUNCH_1D(k_composite_train_bwd, N, 128, "composite_rays_train_backward", grad_weights_sum, grad_image, sigmas,
+    if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_backward: too many rays");
+    NGP_LAUNCH_1D(k_composite_train_bwd, N * 32, 128, "composite_rays_train_backward", grad_weights_sum, grad_image, sigmas,
                   rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
 }
 extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
