@@ -503,6 +503,16 @@ def main():
                    "--cpu-rays", str(args.cpu_rays)], 240)
         line["cpu_baseline"] = r.get("cpu_baseline", {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                                       "sample": "failed: " + str(r.get("unavailable"))})
+    if rank == 0 and world == 1 and not args.no_ref_cuda and not args.unfused:
+        # the unchanged-caller path: module-by-module field (GridEncoder -> FFMLP -> ... as nerf/network_ff.py calls them),
+        # autograd, GradScaler + torch Adam — what a torch-ngp user gets by only swapping the four packages
+        log("drop-in (unfused) path (child process)")
+        torch.cuda.empty_cache()
+        r = child([sys.executable, os.path.join(ROOT, "bench.py"), "--unfused", "--torch-optimizer", "--no-cpu-baseline", "--no-ref-cuda",
+                   "--rays-per-step", str(R), "--steps", "5", "--warmup", "3"], 200)
+        line["dropin_unfused"] = ({"value": r.get("value"), "unit": UNIT, "ms_per_step": r.get("ms_per_step"),
+                                   "what": "same step through the reference-shaped modules only (no fused field, no fused optimizer, no graph)"}
+                                  if "value" in r else r)
     if rank == 0 and world == 1 and not args.no_ref_cuda:
         log("reference CUDA build arm (child process)")
         torch.cuda.empty_cache()
