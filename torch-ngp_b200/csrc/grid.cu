@@ -203,6 +203,14 @@ __device__ __forceinline__ void red_add_h2(__half* addr, __half2 v) {
 __device__ __forceinline__ void red_add_f2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+// two adjacent table entries (C == 2) in one L2 reduction: 8-byte aligned f16x4 / 16-byte aligned f32x4
+__device__ __forceinline__ void red_add_h4(__half* addr, __half2 lo, __half2 hi) {
+    const uint32_t a = *reinterpret_cast<const uint32_t*>(&lo), b = *reinterpret_cast<const uint32_t*>(&hi);
+    asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_f1(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
@@ -286,6 +294,56 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
         const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
         const bool issue = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
 
+        if constexpr (C == 2) {
+            // corners 2j and 2j+1 differ only in x.  When their entries are an aligned adjacent pair (dense level with an
+            // even base index; hashed level with an even x) both are updated by ONE vector reduction (f16x4 / f32x4):
+            // 25 % fewer L2 reduction ops on average.
+#pragma unroll
+            for (uint32_t j = 0; j < (1u << (D - 1)); ++j) {
+                float wyz = 1;
+#pragma unroll
+                for (uint32_t d = 1; d < D; ++d) wyz *= (((2 * j) & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+                // same multiplication order as the reference: ((1 * a0) * a1) * a2
+                float w0 = 1 - pos[0], w1 = pos[0];
+#pragma unroll
+                for (uint32_t d = 1; d < D; ++d) {
+                    const float f = (((2 * j) & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+                    w0 *= f; w1 *= f;
+                }
+                (void)wyz;
+                float v0[2] = {w0 * to_f(g[0]), w0 * to_f(g[1])}, v1[2] = {w1 * to_f(g[0]), w1 * to_f(g[1])};
+                for (uint32_t o = 1; o < maxrun; o <<= 1) {
+#pragma unroll
+                    for (uint32_t c = 0; c < 2; ++c) {
+                        const float t0 = __shfl_up_sync(FULL, v0[c], o), t1 = __shfl_up_sync(FULL, v1[c], o);
+                        if (lane >= my_head + o) { v0[c] += t0; v1[c] += t1; }
+                    }
+                }
+                if (issue) {
+                    const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
+                    const bool pair = ((i0 ^ i1) == 1u);
+                    if constexpr (sizeof(T) == 2) {
+                        const __half2 h0 = __floats2half2_rn(v0[0], v0[1]), h1 = __floats2half2_rn(v1[0], v1[1]);
+                        if (pair) {
+                            red_add_h4(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~1u) * 2), (i0 < i1) ? h0 : h1, (i0 < i1) ? h1 : h0);
+                        } else {
+                            red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i0 * 2), h0);
+                            red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i1 * 2), h1);
+                        }
+                    } else {
+                        if (pair) {
+                            float* dst = reinterpret_cast<float*>(lvl + (size_t)(i0 & ~1u) * 2);
+                            if (i0 < i1) red_add_f4(dst, v0[0], v0[1], v1[0], v1[1]);
+                            else red_add_f4(dst, v1[0], v1[1], v0[0], v0[1]);
+                        } else {
+                            red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i0 * 2), v0[0], v0[1]);
+                            red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i1 * 2), v1[0], v1[1]);
+                        }
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (uint32_t idx = 0; idx < (1u << D); ++idx) {
             float w = 1;
