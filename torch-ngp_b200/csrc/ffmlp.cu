@@ -556,6 +556,14 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             if (!to_inputs)
                 load_tile_rowmajor_async(f_addr[r & 1u], forward_buffer + ((size_t)(num_layers - 1 - r) * B + row0) * HID, TILE_M,
                                          HID, tid, 128, rows_valid);
+            // the first-layer input tile X (operand of wgrad_0 in the tile tail) is staged one round early, while this
+            // round's MMAs run: its buffer F[(n_hidden+1)&1] was last read by the wgrad issued in round n_hidden
+            if (to_inputs) {
+                const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
+                if constexpr (FIELD_COLOR) write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+                else load_tile_rowmajor_async(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+                zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
+            }
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
@@ -644,12 +652,13 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         // dPre_0 was produced in round n_hidden -> G[n_hidden & 1]; H_0 is in F[n_hidden & 1]; X goes to the other F.
         {
             const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
-            if constexpr (FIELD_COLOR) {
-                write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+            if (grad_inputs) {
+                cp_async_wait_all();            // X was staged during the input-gradient round
             } else {
-                load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+                if constexpr (FIELD_COLOR) write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+                else load_tile_rowmajor(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+                zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             }
-            zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
