@@ -559,10 +559,11 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             // the first-layer input tile X (operand of wgrad_0 in the tile tail) is staged one round early, while this
             // round's MMAs run: its buffer F[(n_hidden+1)&1] was last read by the wgrad issued in round n_hidden
             if (to_inputs) {
-                const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
-                if constexpr (FIELD_COLOR) write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
-                else load_tile_rowmajor_async(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
-                zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
+                if constexpr (!FIELD_COLOR) {
+                    const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
+                    load_tile_rowmajor_async(xq, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
+                    zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
+                }
             }
             fence_async_smem();
             fence_before_sync();
@@ -580,6 +581,13 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                     mma_commit(&bar);
                 }
                 __syncwarp();
+            }
+            if constexpr (FIELD_COLOR) {
+                if (to_inputs) {        // [SH | geo | 0] rows for wgrad_0, computed while this round's MMAs execute
+                    const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
+                    write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+                    zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
+                }
             }
             mbar_wait(&bar, phase);
             phase ^= 1u;
