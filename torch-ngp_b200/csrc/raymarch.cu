@@ -203,16 +203,18 @@ __global__ void k_packbits(const float* __restrict__ grid, uint32_t N, float thr
 // arithmetic of the marching loop, and writes it — consecutive lanes write consecutive samples (coalesced), no
 // divergent re-march.  Rays with more than MARCH_K samples fall back to the per-lane second pass.
 static constexpr uint32_t MARCH_K = 64;
+static constexpr uint32_t MARCH_TPB = 64;              // small blocks: the per-ray work is very uneven (sky vs object), 64-thread
+                                                       // CTAs retire sooner and rebalance across SMs
 static constexpr uint32_t MARCH_PITCH = MARCH_K + 1;   // odd pitch: conflict-free reads of one ray's consecutive samples
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MARCH_TPB)
 k_march_rays_train(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                    const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
                    uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears,
                    const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
                    float* __restrict__ deltas, int* __restrict__ rays, int* __restrict__ counter,
                    const float* __restrict__ noises) {
-    __shared__ float tcache[128 * MARCH_PITCH];
+    __shared__ float tcache[MARCH_TPB * MARCH_PITCH];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
     const bool active = n < N;
@@ -574,7 +576,7 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
                                     float* deltas, int32_t* rays, int32_t* counter, const float* noises,
                                     ngp_stream_t stream) {
     if (C < 1 || C > 24) return fail(NGP_EINVAL, "march_rays_train: cascade count out of range");
-    NGP_LAUNCH_1D(k_march_rays_train, N, 128, "march_rays_train", rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
+    NGP_LAUNCH_1D(k_march_rays_train, N, MARCH_TPB, "march_rays_train", rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
                   C, H, M, nears, fars, xyzs, dirs, deltas, rays, counter, noises);
 }
 extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
