@@ -148,7 +148,7 @@ int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
 /* ---- fused NeRF-field extensions (no reference counterpart: they fuse GridEncoder -> FFMLP -> trunc_exp and
  * SHEncoder -> cat -> FFMLP -> sigmoid of nerf/network_ff.py:51-74 so that encoder features, SH features and the
  * concatenated color input never exist in HBM).  Optional fast path; the reference-shaped ops above remain. ---- */
-/* x01 [M,3] f32 in [0,1]; table fp16; writes h_out [M,16] fp16 (sigma-net output), sigma_out [M] f32 = exp(h[:,0])
+/* x01 [M,3] f32 in [0,1]; table fp16; writes h_out [M,16] fp16 (sigma-net output, nullable), sigma_out [M] f32 = exp(h[:,0])
  * (nullable), and when train != 0 the stashes feat_out [M,2L] fp16 and forward_buffer [num_layers,M,64] fp16. */
 int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32_t* offsets, uint32_t L, float S,
                             uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
@@ -172,6 +172,39 @@ int ngp_optim_adam_step(float* params, float* exp_avg, float* exp_avg_sq, void* 
                         uint64_t n, float lr, float beta1, float beta2, float eps, const void* state, int zero_grad,
                         ngp_stream_t stream);
 int ngp_optim_scaler_update(void* state, float growth, float backoff, int growth_interval, ngp_stream_t stream);
+/* ---- occupancy-grid maintenance (replaces the Python/torch op sequences of
+ * nerf/renderer.py:380-442 mark_untrained_grid and :445-538 update_extra_state).  density_grid is float [C, H^3] in Morton
+ * order, bitfield uint8 [C*H^3/8] (the marcher's format, raymarching.cu:279-288).  All random numbers are caller-provided
+ * device arrays (uniform [0,1) floats / integer cell coordinates), so every entry point is a deterministic function;
+ * nothing synchronises with the host. ---- */
+/* poses [B,4,4] f32 camera-to-world; cells covered by no camera get density -1 (renderer.py:440).  count_out [C,H^3] u32
+ * (nullable) = number of covering cameras, n_marked [1] u32 (nullable) += number of cells marked. */
+int ngp_density_grid_mark_untrained(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, float bound,
+                                    uint32_t C, uint32_t H, float* density_grid, uint32_t* count_out, uint32_t* n_marked,
+                                    ngp_stream_t stream);
+/* occ_list [C,H^3] u32: ascending Morton indices of cells with density > 0 (torch.nonzero, renderer.py:495), occ_count [C]. */
+size_t ngp_density_grid_occupied_scratch_bytes(uint32_t C, uint32_t H);
+int ngp_density_grid_occupied(const float* density_grid, uint32_t C, uint32_t H, uint32_t* occ_list, uint32_t* occ_count,
+                              void* scratch, ngp_stream_t stream);
+/* full update (renderer.py:456-483): xyzs [C,H^3,3] = jittered world position of every cell, row = Morton index.
+ * noise [C,H^3,3] (nullable = cell centres) is indexed by the cell's (x*H+y)*H+z, the reference's meshgrid order. */
+int ngp_density_grid_sample_full(uint32_t C, uint32_t H, float bound, const float* noise, float* xyzs, ngp_stream_t stream);
+/* partial update (renderer.py:487-509): per cascade N cells at coords_rand [C,N,3] i32 followed by N cells picked from the
+ * occupied list — by occ_pick_idx [C,N] i64 (the reference's torch.randint(0, Nz)) or, when that is NULL, by
+ * floor(occ_pick_u [C,N] * Nz) with Nz read on the device.  noise [C,2N,3]; xyzs [C,2N,3]; indices [C,2N] u32 (0xffffffff
+ * = no sample: empty occupied list or out-of-range input). */
+int ngp_density_grid_sample_partial(uint32_t C, uint32_t H, float bound, uint32_t N, const int32_t* coords_rand,
+                                    const int64_t* occ_pick_idx, const float* occ_pick_u, const uint32_t* occ_list,
+                                    const uint32_t* occ_count, const float* noise, float* xyzs, uint32_t* indices,
+                                    ngp_stream_t stream);
+/* renderer.py:480-482,511-530: tmp = -1; tmp[cas, indices] = sigmas * density_scale (duplicates keep the largest);
+ * grid = max(grid*decay, tmp) where both >= 0; state[0] = mean(clamp(grid, 0)); state[1] = min(state[0], density_thresh);
+ * bitfield = packbits(grid, state[1]).  sigmas [C,N] f32, indices [C,N] u32 (NULL = identity, N == H^3); tmp_grid [C,H^3]
+ * and scratch (ngp_density_grid_update_scratch_bytes) are workspaces; state [2] f32 stays on the device. */
+size_t ngp_density_grid_update_scratch_bytes(uint32_t C, uint32_t H);
+int ngp_density_grid_update(float* density_grid, float* tmp_grid, const uint32_t* indices, const float* sigmas, uint32_t N,
+                            float density_scale, float decay, float density_thresh, uint32_t C, uint32_t H,
+                            uint8_t* bitfield, float* state, void* scratch, ngp_stream_t stream);
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);

@@ -473,3 +473,41 @@ void oracle_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, in
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
     }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* occupancy-grid maintenance (nerf/renderer.py — torch op sequences restated on scalars)       */
+/* ------------------------------------------------------------------------------------------ */
+/* mark_untrained_grid, renderer.py:380-442.  One cell at a time: world = (2c/(H-1) - 1) * (bound_c - hgs) (:413-419, every
+ * torch op rounds separately; tensor/scalar division on a CUDA device multiplies by the fp32 reciprocal); cam = (world - t) @ R
+ * (:428-429, accumulated with fused multiply-adds in index order — cuBLAS does not document its order, the comparison with
+ * the reference's own output is therefore a count of boundary cells, see tests); masks :432-435; count==0 -> -1 (:440). */
+void oracle_mark_untrained(const float* poses, uint32_t B, double fx, double fy, double cx, double cy, float bound,
+                           uint32_t C, uint32_t H, float* grid, uint32_t* count_out) {
+    const uint32_t H3 = H * H * H;
+    const float inv = 1.0f / (float)(H - 1);
+    const float rx = (float)(cx / fx), ry = (float)(cy / fy);
+    for (uint32_t cas = 0; cas < C; ++cas) {
+        const double bc = fmin((double)(1u << cas), (double)bound);
+        const double hg = bc / (double)H;
+        const float s = (float)(bc - hg), hgs2 = (float)(hg * 2.0);
+#pragma omp parallel for
+        for (uint32_t i = 0; i < H3; ++i) {
+            float w[3];
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t c = oracle_morton3D_invert(i >> d);
+                w[d] = ((2.0f * (float)c) * inv - 1.0f) * s;
+            }
+            uint32_t count = 0;
+            for (uint32_t b = 0; b < B; ++b) {
+                const float* P = poses + (size_t)b * 16;
+                const float dx = w[0] - P[3], dy = w[1] - P[7], dz = w[2] - P[11];
+                const float cxx = fmaf(dz, P[8], fmaf(dy, P[4], dx * P[0]));
+                const float cyy = fmaf(dz, P[9], fmaf(dy, P[5], dx * P[1]));
+                const float czz = fmaf(dz, P[10], fmaf(dy, P[6], dx * P[2]));
+                if (czz > 0.0f && fabsf(cxx) < rx * czz + hgs2 && fabsf(cyy) < ry * czz + hgs2) ++count;
+            }
+            if (count_out) count_out[(size_t)cas * H3 + i] = count;
+            if (count == 0) grid[(size_t)cas * H3 + i] = -1.0f;
+        }
+    }
+}

@@ -42,3 +42,26 @@ def synth_rays(N, seed=3, device="cpu"):
     grid, fill = S.box_union_density(128, seed=12)
     bitfield = torch.from_numpy(S.packbits_np(grid.numpy()))
     return rays_o.to(device), rays_d.to(device), bitfield.to(device), grid
+
+
+# ---- occupancy-grid fixtures -------------------------------------------------------------------
+def lex_to_morton(H):
+    """Morton index of the cells in the reference's meshgrid (x-major) enumeration."""
+    from oracle.density_grid_oracle import morton3d
+    xs, ys, zs = [a.reshape(-1).astype(np.uint32) for a in np.meshgrid(np.arange(H), np.arange(H), np.arange(H), indexing="ij")]
+    return morton3d(xs, ys, zs)
+
+
+def check_duplicates_aware(new, ref, before, indices, sigmas, decay):
+    """cells sampled once must agree exactly; for cells drawn several times the reference keeps an arbitrary sample, the oracle
+    the largest: the reference value must be the EMA of ONE of the candidates."""
+    C, H3 = new.shape
+    for cas in range(C):
+        diff = np.nonzero(new[cas] != ref[cas])[0]
+        for cell in diff:
+            cand = np.asarray(sigmas[cas], np.float32)[np.asarray(indices[cas]) == cell]
+            assert len(cand) > 1, f"cell {cell} sampled once but differs"
+            allowed = np.maximum(before[cas, cell] * np.float32(decay), cand)
+            assert ref[cas, cell] in allowed
+            assert new[cas, cell] == allowed.max()
+    return sum(int((new[c] != ref[c]).sum()) for c in range(C))

@@ -35,6 +35,11 @@ _SIGNATURES = {
     "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
     "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],
     "ngp_optim_scaler_update": [_vp, _f32, _f32, _i32, _vp],
+    "ngp_density_grid_mark_untrained": [_vp, _u32, _f32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _vp, _vp, _vp],
+    "ngp_density_grid_occupied": [_vp, _u32, _u32, _vp, _vp, _vp, _vp],
+    "ngp_density_grid_sample_full": [_u32, _u32, _f32, _vp, _vp, _vp],
+    "ngp_density_grid_sample_partial": [_u32, _u32, _f32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_density_grid_update": [_vp, _vp, _vp, _vp, _u32, _f32, _f32, _f32, _u32, _u32, _vp, _vp, _vp, _vp],
     "ngp_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "ngp_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
     "ngp_morton3D": [_vp, _u32, _vp, _vp],
@@ -48,7 +53,8 @@ _SIGNATURES = {
 }
 # every symbol include/ngp_b200.h declares (tests check the .so exports all of them)
 EXPORTED = sorted(list(_SIGNATURES) + ["ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
-                                       "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes"])
+                                       "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes",
+                                       "ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"])
 
 _lib = None
 
@@ -74,6 +80,9 @@ def load():
     lib.ngp_reset_launch_count.restype = None
     lib.ngp_ffmlp_backward_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32, _u32]
     lib.ngp_ffmlp_backward_workspace_bytes.restype = _sz
+    for name in ("ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"):
+        getattr(lib, name).argtypes = [_u32, _u32]
+        getattr(lib, name).restype = _sz
     _lib = lib
     return lib
 

@@ -295,7 +295,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
 #pragma unroll
                 for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                 if (row_ok) {
-                    if constexpr (OUT_MODE != OUT_RGB) {
+                    if constexpr (OUT_MODE != OUT_RGB) if (outputs) {
                         uint4* o = reinterpret_cast<uint4*>(outputs + row * OUT_PAD);
                         o[0] = make_uint4(p[0], p[1], p[2], p[3]);
                         o[1] = make_uint4(p[4], p[5], p[6], p[7]);

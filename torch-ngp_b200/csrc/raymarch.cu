@@ -17,30 +17,12 @@
 #include "common.cuh"
 #include <float.h>
 
+#include "morton.cuh"
+
 namespace ngp {
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
 __device__ __forceinline__ float signf1(float x) { return copysignf(1.0f, x); }
-
-// 10-bit x 3 Morton code (bit interleave by magic multiplies)
-__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
-__host__ __device__ __forceinline__ uint32_t morton_enc(uint32_t x, uint32_t y, uint32_t z) {
-    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
-}
-__host__ __device__ __forceinline__ uint32_t compact3(uint32_t x) {
-    x &= 0x49249249u;
-    x = (x | (x >> 2)) & 0xc30c30c3u;
-    x = (x | (x >> 4)) & 0x0f00f00fu;
-    x = (x | (x >> 8)) & 0xff0000ffu;
-    x = (x | (x >> 16)) & 0x0000ffffu;
-    return x;
-}
 
 // cascade level from position / step size (raymarching.cu:42-54)
 __device__ __forceinline__ int mip_from_pos(float x, float y, float z, float max_cascade) {

@@ -16,6 +16,7 @@ from gridencoder import GridEncoder
 from shencoder import SHEncoder
 from ffmlp import FFMLP
 import raymarching
+import density_grid as _density_grid
 
 
 class _trunc_exp(torch.autograd.Function):
@@ -59,7 +60,11 @@ class NeRFFieldFF(nn.Module):
                                hidden_dim=hidden_dim_color, num_layers=num_layers_color)
         aabb = torch.FloatTensor([-bound, -bound, -bound, bound, bound, bound])
         self.register_buffer('aabb_train', aabb)
+        self.cuda_ray = True
+        self.register_buffer('density_grid', torch.zeros(self.cascade, grid_size ** 3))
         self.register_buffer('density_bitfield', torch.zeros(self.cascade * grid_size ** 3 // 8, dtype=torch.uint8))
+        self.mean_density = 0
+        self.iter_density = 0
         self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
         self.mean_count = 0
         self.local_step = 0
@@ -103,6 +108,47 @@ class NeRFFieldFF(nn.Module):
         image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return {'image': image, 'depth': depth, 'weights_sum': weights_sum, 'n_samples': xyzs.shape[0]}
+
+    # occupancy-grid maintenance: the fused kernels (density_grid.py) ...
+    mark_untrained_grid = _density_grid.mark_untrained_grid
+    update_extra_state = _density_grid.update_extra_state
+
+    # ... and the reference's op-by-op torch sequence (renderer.py:445-530), restated for parity tests and timing
+    @torch.no_grad()
+    def update_extra_state_unfused(self, decay=0.95):
+        H, dev = self.grid_size, self.density_bitfield.device
+        fresh = torch.full_like(self.density_grid, -1)
+
+        def query(cas, cells, slots):
+            scale = min(2 ** cas, self.bound)
+            half = scale / H
+            pts = (2 * cells.float() / (H - 1) - 1) * (scale - half)
+            pts += (torch.rand_like(pts) * 2 - 1) * half
+            sig = self.density(pts)['sigma'].reshape(-1).detach().float()
+            sig *= self.density_scale
+            fresh[cas, slots] = sig
+
+        if self.iter_density < 16:
+            ax = torch.arange(H, dtype=torch.int32, device=dev)
+            cells = torch.stack(torch.meshgrid(ax, ax, ax, indexing='ij'), dim=-1).reshape(-1, 3)
+            slots = raymarching.morton3D(cells).long()
+            for cas in range(self.cascade):
+                query(cas, cells, slots)
+        else:
+            n = H ** 3 // 4
+            for cas in range(self.cascade):
+                cells = torch.randint(0, H, (n, 3), device=dev)
+                slots = raymarching.morton3D(cells).long()
+                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                occ = occ[torch.randint(0, occ.shape[0], [n], dtype=torch.long, device=dev)]
+                query(cas, torch.cat([cells, raymarching.morton3D_invert(occ)], dim=0), torch.cat([slots, occ], dim=0))
+        both = (self.density_grid >= 0) & (fresh >= 0)
+        self.density_grid[both] = torch.maximum(self.density_grid[both] * decay, fresh[both])
+        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        self.iter_density += 1
+        self.density_bitfield = raymarching.packbits(self.density_grid, min(self.mean_density, self.density_thresh),
+                                                     self.density_bitfield)
+        self.update_mean_count()
 
     def update_mean_count(self):
         """tail of renderer.py update_extra_state (:532-536)."""
