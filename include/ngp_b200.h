@@ -205,6 +205,18 @@ size_t ngp_density_grid_update_scratch_bytes(uint32_t C, uint32_t H);
 int ngp_density_grid_update(float* density_grid, float* tmp_grid, const uint32_t* indices, const float* sigmas, uint32_t N,
                             float density_scale, float decay, float density_thresh, uint32_t C, uint32_t H,
                             uint8_t* bitfield, float* state, void* scratch, ngp_stream_t stream);
+/* ---- ray generation + training-pixel gather (replaces the torch op sequences of
+ * nerf/utils.py:54-137 get_rays, nerf/provider.py:308-312 and nerf/utils.py:494-508). ---- */
+/* poses [B,4,4] f32 camera-to-world; inds [*,N] i64 pixel indices (row stride inds_stride: 0 = one list shared by all
+ * cameras; NULL = all H*W pixels in order, N == H*W); rays_o / rays_d [B,N,3] f32 (directions normalised). */
+int ngp_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W, uint32_t N,
+                 const int64_t* inds, uint32_t inds_stride, float* rays_o, float* rays_d, ngp_stream_t stream);
+/* images [n_img,H,W,C] (dtype 0 = f32, 2 = u8 scaled by 1/255; C = 3 or 4), image_index [B] i64 (NULL = camera b uses image
+ * b).  pixels_out [B,N,C] (nullable) = raw gather; gt_out [B,N,3] (nullable) = target colour: sRGB->linear when linear != 0,
+ * then rgb*a + bg*(1-a) when C == 4, bg = bg_pixels [B,N,3] or, when that is NULL, bg_scalar. */
+int ngp_gather_pixels(const void* images, int dtype, const int64_t* image_index, uint32_t H, uint32_t W, uint32_t C, uint32_t B,
+                      uint32_t N, const int64_t* inds, uint32_t inds_stride, int linear, const float* bg_pixels,
+                      float bg_scalar, float* pixels_out, float* gt_out, ngp_stream_t stream);
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);

@@ -108,3 +108,38 @@ def test_fused_train_step_matches_autograd_path():
     assert float((ea - eb).abs().max()) <= 2.5e-2                      # at most a sign flip on near-zero gradients (2*lr)
     assert float(((ea - eb).abs() > 1e-3).float().mean()) < 5e-3       # ...and only for a tiny fraction of entries
     assert float((wa - wb).abs().max()) <= 2.5e-2
+
+
+def test_resume_from_reference_adam_state():
+    """FusedFieldOptimizer.load_state_dict(torch Adam state in the reference's group layout) then one fused step == torch Adam's
+    next step from the same state (checkpoint interchange, nerf/utils.py:1118-1137)."""
+    from nerf_step import NeRFFieldFF
+    from ngp_optim import FusedFieldOptimizer
+    torch.manual_seed(0)
+    a = NeRFFieldFF().cuda()
+    b = NeRFFieldFF().cuda()
+    b.load_state_dict(a.state_dict())
+    pa = [a.encoder.embeddings, a.sigma_net.weights, a.color_net.weights]
+    ref = torch.optim.Adam([{"params": [pa[0]]}, {"params": [pa[1]]}, {"params": []}, {"params": [pa[2]]}], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    grads = [[(torch.randn(p.shape, generator=gen(50 + 3 * it + i)) * 1e-3).cuda() for i, p in enumerate(pa)] for it in range(4)]
+    for it in range(3):
+        for p, g in zip(pa, grads[it]):
+            p.grad = g.clone()
+        ref.step()
+    b.load_state_dict(a.state_dict())
+    fused = FusedFieldOptimizer(b.encoder, b.sigma_net, b.color_net)
+    fused.load_state_dict(ref.state_dict())
+    fused.load_scaler_state_dict({"scale": 1024.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 0})
+    for p, g in zip(pa, grads[3]):
+        p.grad = (g * 1024.0).half().float() / 1024.0          # what the fp16 sink can represent
+    ref.step()
+    for (p, off, k), g in zip(fused.segments, grads[3]):
+        fused.sink[off:off + k].copy_((g * 1024.0).half().reshape(-1))
+    fused.step()
+    pb = [b.encoder.embeddings, b.sigma_net.weights, b.color_net.weights]
+    for x, y in zip(pa, pb):
+        assert rel_err(y.detach().cpu().numpy(), x.detach().cpu().numpy()) < 1e-5
+    sd = fused.state_dict()
+    assert float(sd["state"][0]["step"]) == 4.0
+    assert rel_err(sd["state"][2]["exp_avg_sq"].cpu().numpy(), ref.state_dict()["state"][2]["exp_avg_sq"].cpu().numpy()) < 1e-5
+    fused.detach()

@@ -59,3 +59,52 @@ class FusedFieldOptimizer:
                           self.state.data_ptr(), 1)
         _backend.call("ngp_optim_scaler_update", self.state.data_ptr(), float(self.growth), float(self.backoff),
                       int(self.growth_interval))
+
+    # ---- checkpoint interchange with the reference trainer (nerf/utils.py:1015-1136) --------------------------------
+    # The reference builds torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15) with the groups
+    # [encoder], [sigma_net], [encoder_dir] (no parameters), [color_net] (network_ff.py:137-149) and a torch.amp.GradScaler.
+    def state_dict(self):
+        """torch.optim.Adam-format state dict for the reference's parameter-group layout (loadable by its trainer)."""
+        step = int(self.state[3].item())
+        state = {}
+        for i, (p, off, k) in enumerate(self.segments):
+            state[i] = {"step": torch.tensor(float(step)),
+                        "exp_avg": self.exp_avg[off:off + k].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p).clone()}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False)
+        groups = [dict(group, params=ids) for ids in ([0], [1], [], [2])]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        """Accepts the reference trainer's Adam state (parameters numbered in get_params order: embeddings, sigma, color)."""
+        ids = [i for g in sd["param_groups"] for i in g["params"]]
+        if len(ids) != len(self.segments):
+            raise RuntimeError(f"FusedFieldOptimizer: checkpoint has {len(ids)} parameters, expected {len(self.segments)}")
+        steps = set()
+        for i, (p, off, k) in zip(ids, self.segments):
+            st = sd["state"].get(i)
+            if st is None:                       # parameter never stepped
+                self.exp_avg[off:off + k].zero_(); self.exp_avg_sq[off:off + k].zero_(); steps.add(0)
+                continue
+            if st["exp_avg"].numel() != k:
+                raise RuntimeError("FusedFieldOptimizer: optimizer state shape mismatch")
+            self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        if len(steps) != 1:
+            raise RuntimeError("FusedFieldOptimizer: parameters with different step counts are not supported")
+        self.state[3] = steps.pop()
+        g0 = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+
+    def scaler_state_dict(self):
+        """torch.amp.GradScaler.state_dict() format."""
+        return {"scale": float(self.scale_tensor().item()), "growth_factor": self.growth, "backoff_factor": self.backoff,
+                "growth_interval": self.growth_interval, "_growth_tracker": int(self.state[1].item())}
+
+    def load_scaler_state_dict(self, sd):
+        self.scale_tensor().fill_(float(sd["scale"]))
+        self.state[1] = int(sd["_growth_tracker"])
+        self.growth, self.backoff, self.growth_interval = sd["growth_factor"], sd["backoff_factor"], sd["growth_interval"]
+
