@@ -24,6 +24,7 @@
 //     MN-major (the same row-major activation tiles, no transposes), M=64 N=64, fp32 TMEM
 //     accumulators persistent across the CTA's row tiles, then one fp32 red.add per element.
 #include "common.cuh"
+#include <stdlib.h>
 #include "umma.cuh"
 #include "mlp_common.cuh"
 #include "grid.cuh"
@@ -90,20 +91,19 @@ __device__ __forceinline__ void sh4_eval(float x, float y, float z, float out[16
 }
 
 // color-net input row [SH4 | geo(15) | 0] -> 4 x 16-byte chunks of the swizzled tile row `r`
-__device__ __forceinline__ void write_shgeo_row(uint32_t tile_addr, uint32_t r, bool ok, const float* __restrict__ dirs,
-                                                const __half* __restrict__ h_sigma, size_t row) {
+// SH(dir) | geo | pad row of the color net's input tile from values already in registers
+__device__ __forceinline__ void write_shgeo_row_regs(uint32_t tile_addr, uint32_t r, bool ok, float dx, float dy, float dz,
+                                                     const uint4 h0, const uint4 h1) {
     uint4 c[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (ok) {
         float sh[16];
-        sh4_eval(__ldg(dirs + row * 3), __ldg(dirs + row * 3 + 1), __ldg(dirs + row * 3 + 2), sh);
+        sh4_eval(dx, dy, dz, sh);
         uint32_t p[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) p[i] = pack_h2(sh[2 * i], sh[2 * i + 1]);
         c[0] = make_uint4(p[0], p[1], p[2], p[3]);
         c[1] = make_uint4(p[4], p[5], p[6], p[7]);
         // geo = h[1..15] shifted down by one half; last lane of the row is the zero pad (network_ff.py:67)
-        const uint4 h0 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16));
-        const uint4 h1 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16) + 1);
         const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         uint32_t g[8];
 #pragma unroll
@@ -114,19 +114,31 @@ __device__ __forceinline__ void write_shgeo_row(uint32_t tile_addr, uint32_t r, 
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) st_shared_v4(tile_addr + sw128_off(r, k), c[k]);
 }
+__device__ __forceinline__ void write_shgeo_row(uint32_t tile_addr, uint32_t r, bool ok, const float* __restrict__ dirs,
+                                                const __half* __restrict__ h_sigma, size_t row) {
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+    if (ok) {
+        dx = __ldg(dirs + row * 3); dy = __ldg(dirs + row * 3 + 1); dz = __ldg(dirs + row * 3 + 2);
+        h0 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16));
+        h1 = __ldg(reinterpret_cast<const uint4*>(h_sigma + row * 16) + 1);
+    }
+    write_shgeo_row_regs(tile_addr, r, ok, dx, dy, dz, h0, h1);
+}
 
 struct LevelParams { uint32_t off, size, res; float scale; };
 
 // hash-grid features of one sample -> swizzled tile row (+ optional global stash); D=3, C=2, fp16 table, linear interp
+// (`xin` = the sample's coordinates, loaded by the caller one tile ahead so the gathers do not wait on them)
 __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, bool ok, const FieldArgs& fa,
-                                               const LevelParams* __restrict__ lv, size_t row) {
+                                               const LevelParams* __restrict__ lv, size_t row, const float (&xin)[3]) {
     float x[3] = {0.5f, 0.5f, 0.5f};
     bool oob = !ok;
     if (ok) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             // GridEncoder.forward: (inputs + bound) / (2 * bound); torch divides by a scalar as a multiply by 1/s
-            x[d] = (__ldg(fa.xyz + row * 3 + d) + fa.bound) * fa.inv_2bound;
+            x[d] = (xin[d] + fa.bound) * fa.inv_2bound;
             if (x[d] < 0 || x[d] > 1) oob = true;
         }
     }
@@ -224,13 +236,29 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
     uint32_t phase = 0;
 
     const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
+    // IN_GRID: the coordinates of the next tile's sample are loaded a tile ahead (the gathers depend on them)
+    float nx_x[3] = {0.f, 0.f, 0.f};
+    auto preload_xyz = [&](uint32_t t) {
+        if constexpr (IN_MODE == IN_GRID) {
+            const size_t rw = (size_t)t * TILE_M + tid;
+            if (t < ntiles && rw < (size_t)B) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) nx_x[d] = __ldg(fa.xyz + rw * 3 + d);
+            }
+        }
+    };
+    preload_xyz(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
         const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
         const bool row_ok = tid < rows_valid;
         // input tile -> A operand
-        if constexpr (IN_MODE == IN_GRID) write_grid_row(a_addr, tid, row_ok, fa, lv, row);
+        if constexpr (IN_MODE == IN_GRID) {
+            const float cur_x[3] = {nx_x[0], nx_x[1], nx_x[2]};
+            preload_xyz(tile + gridDim.x);
+            write_grid_row(a_addr, tid, row_ok, fa, lv, row, cur_x);
+        }
         else if constexpr (IN_MODE == IN_SHGEO) write_shgeo_row(a_addr, tid, row_ok, fa.dirs, fa.h_sigma, row);
         else load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
 
@@ -515,11 +543,49 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
 
     const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     const uint32_t nrounds = 1 + n_hidden + (grad_inputs ? 1u : 0u);
+    // FIELD_COLOR: the per-row scalars a tile needs (rgb, d_rgb for dL/dy; dirs, h_sigma, d_sigma for the tail) are loaded
+    // one tile ahead into registers, so no round waits on a dependent global load
+    float nx_y[3] = {0.f, 0.f, 0.f}, nx_g[3] = {0.f, 0.f, 0.f}, nx_dir[3] = {0.f, 0.f, 0.f}, nx_dsig = 0.f;
+    uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
+    auto preload_rows = [&](uint32_t t) {
+        if constexpr (FIELD_COLOR) {
+            const size_t rw = (size_t)t * TILE_M + tid;
+            if (t < ntiles && rw < (size_t)B) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    nx_y[c] = __ldg(fa.rgb + rw * 3 + c);
+                    nx_g[c] = __ldg(fa.d_rgb + rw * 3 + c);
+                    nx_dir[c] = __ldg(fa.dirs + rw * 3 + c);
+                }
+                nx_dsig = __ldg(fa.d_sigma + rw);
+                nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
+                nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
+            }
+        }
+    };
+    preload_rows(blockIdx.x);
+    // plain variant: the dL/dy tile (2 x 16 bytes per thread) likewise travels one tile ahead in registers
+    uint4 nx_dy[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    auto preload_dy = [&](uint32_t t) {
+        if constexpr (!FIELD_COLOR) {
+#pragma unroll
+            for (uint32_t k = 0; k < 2; ++k) {
+                const uint32_t g = tid + k * 128u;
+                const size_t rw = (size_t)t * TILE_M + (g >> 1);
+                nx_dy[k] = (t < ntiles && rw < (size_t)B) ? __ldg(reinterpret_cast<const uint4*>(grad + rw * OUT_PAD) + (g & 1u))
+                                                           : make_uint4(0, 0, 0, 0);
+            }
+        }
+    };
+    preload_dy(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
         const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
         const bool row_ok = tid < rows_valid;
+        float cur_dir[3] = {nx_dir[0], nx_dir[1], nx_dir[2]};
+        const float cur_dsig = nx_dsig;
+        const uint4 cur_h0 = nx_h0, cur_h1 = nx_h1;
         // dL/dy -> G1 (K-major A of round 0 and, zero-padded to 64 columns, MN-major operand of the output-layer wgrad)
         if constexpr (FIELD_COLOR) {
             // dL/dh = half(d_rgb) * y (1 - y), y = rgb (already fp16-representable); columns 3..63 are zero
@@ -528,18 +594,24 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 float dh[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float y = __ldg(fa.rgb + row * 3 + c);
-                    const float g = __half2float(__float2half_rn(__ldg(fa.d_rgb + row * 3 + c)));
+                    const float y = nx_y[c];
+                    const float g = __half2float(__float2half_rn(nx_g[c]));
                     dh[c] = g * (y * (1.0f - y));
                 }
                 q0 = pack_h2(dh[0], dh[1]);
                 q1 = pack_h2(dh[2], 0.f);
             }
+            preload_rows(tile + gridDim.x);      // next tile's rows: in flight during this tile's rounds
             st_shared_v4(g_addr[1] + sw128_off(tid, 0), make_uint4(q0, q1, 0, 0));
 #pragma unroll
             for (uint32_t c = 1; c < 8; ++c) st_shared_v4(g_addr[1] + sw128_off(tid, c), make_uint4(0, 0, 0, 0));
         } else {
-            load_tile_rowmajor(g_addr[1], grad + row0 * OUT_PAD, TILE_M, OUT_PAD, tid, 128, rows_valid);
+#pragma unroll
+            for (uint32_t k = 0; k < 2; ++k) {
+                const uint32_t g = tid + k * 128u;
+                st_shared_v4(g_addr[1] + sw128_off(g >> 1, g & 1u), nx_dy[k]);
+            }
+            preload_dy(tile + gridDim.x);
             zero_tile_cols(g_addr[1], TILE_M, OUT_PAD >> 3, tid, 128);
         }
 
@@ -553,9 +625,11 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             // this round's forward activations (ReLU mask + wgrad operand): coalesced rows -> F[r&1] (free: its last
             // reader, the wgrad issued in round r-1, completed with that round's commit)
             // ... fetched with cp.async so the copy overlaps the MMAs of this round
+            // (requesting round r+1's tile one round early, right after round r's MMAs complete, measured no better: with two
+            //  CTAs per SM the copy latency is already covered by the sibling CTA)
             if (!to_inputs)
-                load_tile_rowmajor_async(f_addr[r & 1u], forward_buffer + ((size_t)(num_layers - 1 - r) * B + row0) * HID, TILE_M,
-                                         HID, tid, 128, rows_valid);
+                load_tile_rowmajor_async(f_addr[r & 1u], forward_buffer + ((size_t)(num_layers - 1 - r) * B + row0) * HID, TILE_M, HID, tid,
+                                         128, rows_valid);
             // the first-layer input tile X (operand of wgrad_0 in the tile tail) is staged one round early, while this
             // round's MMAs run: its buffer F[(n_hidden+1)&1] was last read by the wgrad issued in round n_hidden
             if (to_inputs) {
@@ -621,8 +695,8 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 tmem_ld16(t_lane + 16, v);
                 tmem_ld_wait();
                 if (row_ok) {
-                    const float h0 = __half2float(__ldg(fa.h_sigma + row * 16));
-                    const float g0 = __ldg(fa.d_sigma + row) * expf(fminf(fmaxf(h0, -15.f), 15.f));
+                    const float h0 = __low2float(*reinterpret_cast<const __half2*>(&cur_h0.x));
+                    const float g0 = cur_dsig * expf(fminf(fmaxf(h0, -15.f), 15.f));
                     uint32_t p[8];
                     p[0] = pack_h2(g0, __uint_as_float(v[0]));
 #pragma unroll
@@ -655,7 +729,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
             if constexpr (FIELD_COLOR) {
                 // (staging these rows earlier, inside the input-gradient round, measured slower: 1.47 vs 1.35 ms)
-                write_shgeo_row(xq, tid, row_ok, fa.dirs, fa.h_sigma, row);
+                write_shgeo_row_regs(xq, tid, row_ok, cur_dir[0], cur_dir[1], cur_dir[2], cur_h0, cur_h1);
                 zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             } else if (grad_inputs) {
                 cp_async_wait_all();            // X was staged (cp.async) during the input-gradient round
