@@ -248,6 +248,21 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
         }
     };
     preload_xyz(blockIdx.x);
+    // IN_SHGEO: likewise the direction and the sigma-net output row of the next tile
+    float nx_d[3] = {0.f, 0.f, 0.f};
+    uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
+    auto preload_shgeo = [&](uint32_t t) {
+        if constexpr (IN_MODE == IN_SHGEO) {
+            const size_t rw = (size_t)t * TILE_M + tid;
+            if (t < ntiles && rw < (size_t)B) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) nx_d[d] = __ldg(fa.dirs + rw * 3 + d);
+                nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
+                nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
+            }
+        }
+    };
+    preload_shgeo(blockIdx.x);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * TILE_M;
         const size_t row = row0 + tid;
@@ -259,7 +274,12 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
             preload_xyz(tile + gridDim.x);
             write_grid_row(a_addr, tid, row_ok, fa, lv, row, cur_x);
         }
-        else if constexpr (IN_MODE == IN_SHGEO) write_shgeo_row(a_addr, tid, row_ok, fa.dirs, fa.h_sigma, row);
+        else if constexpr (IN_MODE == IN_SHGEO) {
+            const float cd0 = nx_d[0], cd1 = nx_d[1], cd2 = nx_d[2];
+            const uint4 ch0 = nx_h0, ch1 = nx_h1;
+            preload_shgeo(tile + gridDim.x);
+            write_shgeo_row_regs(a_addr, tid, row_ok, cd0, cd1, cd2, ch0, ch1);
+        }
         else load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
 
         for (uint32_t l = 0; l < nmat; ++l) {
