@@ -75,3 +75,41 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _occ_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "torch-ngp_b200")]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import types
+    import ngp_dp
+    torch.manual_seed(100 + rank)                      # diverged per-rank RNG, as in training
+    m = types.SimpleNamespace(density_grid=torch.rand(2, 64), density_bitfield=(torch.rand(16) * 255).to(torch.uint8),
+                              mean_density=float(rank) + 0.25)
+    ngp_dp.sync_occupancy(m, src=0)
+    st = ngp_dp.seed_lock(step=48)
+    locked = torch.rand(4)
+    ngp_dp.seed_unlock(st)
+    after = torch.rand(4)                               # the per-rank stream continues where it was
+    q.put((rank, m.density_grid.clone(), m.density_bitfield.clone(), m.mean_density, locked, after))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_occupancy_sync_and_seed_lock():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 17) % 1000
+    procs = [ctx.Process(target=_occ_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, g0, b0, md0, l0, a0), (_, g1, b1, md1, l1, a1) = res
+    assert torch.equal(g0, g1) and torch.equal(b0, b1) and md0 == md1 == 0.25
+    assert torch.equal(l0, l1)                          # locked draws identical on both ranks
+    assert not torch.equal(a0, a1)                      # per-rank streams restored
+

@@ -67,3 +67,34 @@ def broadcast_module(module, src=0, group=None):
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src=src, group=group)
+
+
+def sync_occupancy(model, src=0, group=None):
+    """Keep the replicas' occupancy state identical after a rank-local update_extra_state (the update draws random
+    sample positions, so replicas diverge unless the RNG streams are locked): broadcast density_grid (8 MB per cascade) and
+    density_bitfield (256 KB per cascade) from `src`, plus mean_density.  Call it right after update_extra_state, i.e. every 16
+    steps; alternatively call seed_lock() before the update on every rank and skip the broadcast."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    dist.broadcast(model.density_grid, src=src, group=group)
+    dist.broadcast(model.density_bitfield, src=src, group=group)
+    md = torch.tensor([float(model.mean_density)], dtype=torch.float64, device=model.density_grid.device)
+    dist.broadcast(md, src=src, group=group)
+    model.mean_density = float(md.item())
+
+
+def seed_lock(step, base_seed=0):
+    """Give every rank the same RNG stream for the next update_extra_state (identical weights + identical draws = identical
+    grids, no exchange needed).  Returns the previous CPU / CUDA generator states so the caller can restore its per-rank stream."""
+    cpu_state = torch.get_rng_state()
+    cuda_state = torch.cuda.get_rng_state() if torch.cuda.is_available() else None
+    torch.manual_seed(base_seed * 1000003 + int(step))
+    return cpu_state, cuda_state
+
+
+def seed_unlock(states):
+    cpu_state, cuda_state = states
+    torch.set_rng_state(cpu_state)
+    if cuda_state is not None:
+        torch.cuda.set_rng_state(cuda_state)
+
