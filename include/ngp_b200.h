@@ -217,6 +217,12 @@ int ngp_get_rays(const float* poses, uint32_t B, float fx, float fy, float cx, f
 int ngp_gather_pixels(const void* images, int dtype, const int64_t* image_index, uint32_t H, uint32_t W, uint32_t C, uint32_t B,
                       uint32_t N, const int64_t* inds, uint32_t inds_stride, int linear, const float* bg_pixels,
                       float bg_scalar, float* pixels_out, float* gt_out, ngp_stream_t stream);
+/* ---- frequency encoding (freqencoder/src/freqencoder.h:6-9; not on the --ff path, built for breadth) ----
+ * inputs [B,D] f32 -> outputs [B,C] f32, C = D + 2*deg*D: [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] in D-wide blocks. */
+int ngp_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C, float* outputs,
+                            ngp_stream_t stream);
+int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                             float* grad_inputs, ngp_stream_t stream);
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);

@@ -288,3 +288,24 @@ def sh_encode(dirs, degree):
                 v = np.sqrt(2) * Y.imag
             out[:, l * l + l + m] = v
     return out
+
+
+# ---- frequency encoding (freqencoder/src/freqencoder.cu:28-104; same layout as the reference's pure-PyTorch FreqEncoder, encoding.py:5-42)
+def freq_encode(x, degree):
+    """[B,D] -> [B, D + 2*degree*D] = [x, sin(2^0 x), cos(2^0 x), ...] (float64 sin/cos rounded to fp32)."""
+    x = _c32(x)
+    out = [x]
+    for f in range(degree):
+        a = (x * np.float32(2.0 ** f)).astype(np.float64)
+        out += [np.sin(a).astype(np.float32), np.cos(a).astype(np.float32)]
+    return np.concatenate(out, axis=-1)
+
+
+def freq_encode_backward(grad, outputs, D, degree):
+    """:66-104 — grad_x = g_x + sum_f 2^f (g_sin * cos - g_cos * sin), sin/cos taken from the forward outputs."""
+    g = np.asarray(grad, np.float64); y = np.asarray(outputs, np.float64)
+    res = g[:, :D].copy()
+    for f in range(degree):
+        s0 = D + 2 * f * D
+        res += (2.0 ** f) * (g[:, s0:s0 + D] * y[:, s0 + D:s0 + 2 * D] - g[:, s0 + D:s0 + 2 * D] * y[:, s0:s0 + D])
+    return res.astype(np.float32)

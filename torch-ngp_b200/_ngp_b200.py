@@ -42,6 +42,8 @@ _SIGNATURES = {
     "ngp_density_grid_update": [_vp, _vp, _vp, _vp, _u32, _f32, _f32, _f32, _u32, _u32, _vp, _vp, _vp, _vp],
     "ngp_get_rays": [_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _u32, _vp, _u32, _vp, _vp, _vp],
     "ngp_gather_pixels": [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _vp, _u32, _i32, _vp, _f32, _vp, _vp, _vp],
+    "ngp_freq_encode_forward": [_vp, _u32, _u32, _u32, _u32, _vp, _vp],
+    "ngp_freq_encode_backward": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "ngp_near_far_from_aabb": [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp],
     "ngp_sph_from_ray": [_vp, _vp, _f32, _u32, _vp, _vp],
     "ngp_morton3D": [_vp, _u32, _vp, _vp],
