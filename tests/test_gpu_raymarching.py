@@ -234,3 +234,30 @@ def test_vs_reference_extension():
     rx, rdd, rl = R.march_rays(N, 2, alive, rt, ro, rd, 1.0, bf, 1, 128, rn, rf, nz0, 128)
     x, d, l = raymarching.march_rays(N, 2, alive, rt, ro, rd, 1, bf, 1, 128, rn, rf, 128, False, 0, 1024)
     assert torch.equal(x, rx) and torch.equal(l, rl) and torch.equal(d, rdd)
+
+
+def test_time_indexed_bitfield_slices():
+    """D-NeRF keeps [T, ...] occupancy state and hands slices to the same ops (dnerf/renderer.py:92-93, 295, 362, 546-547):
+    packbits must write through a slice view, the marchers must read one."""
+    import raymarching
+    import ngp_synth as S
+    T, H = 4, 128
+    grid, _ = S.box_union_density(H, seed=12)
+    grids = torch.zeros(T, 1, H ** 3, device="cuda")
+    grids[2] = grid.cuda()
+    bits = torch.zeros(T, H ** 3 // 8, dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        out = raymarching.packbits(grids[t], 0.01, bits[t])
+        assert out.data_ptr() == bits[t].data_ptr()
+    ref = torch.from_numpy(S.packbits_np(grid.numpy())).cuda()
+    assert torch.equal(bits[2], ref) and int(bits[0].sum()) == 0 and int(bits[3].sum()) == 0
+    rays_o, rays_d, _, _ = synth_rays(2048)
+    ro, rd = rays_o.cuda(), rays_d.cuda()
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1.0], device="cuda")
+    nears, fars = raymarching.near_far_from_aabb(ro, rd, aabb, 0.2)
+    a = raymarching.march_rays_train(ro, rd, 1, bits[2], 1, H, nears, fars, None, -1, False, 128, True, 0, 1024)
+    b = raymarching.march_rays_train(ro, rd, 1, ref.clone(), 1, H, nears, fars, None, -1, False, 128, True, 0, 1024)
+    assert a[0].shape == b[0].shape and a[0].shape[0] > 0
+    assert (gather_segments(a[0].cpu().numpy(), a[3].cpu().numpy()) == gather_segments(b[0].cpu().numpy(), b[3].cpu().numpy())).all()
+    e = raymarching.march_rays_train(ro, rd, 1, bits[0], 1, H, nears, fars, None, -1, False, 128, True, 0, 1024)
+    assert int(e[3][:, 2].sum()) == 0                     # empty time slice: no samples
