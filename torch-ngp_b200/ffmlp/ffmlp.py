@@ -1,140 +1,63 @@
-"""ffmlp — drop-in for the reference's ffmlp/ffmlp.py (FFMLP :99-168, _ffmlp_forward :15-83).
+"""ffmlp.ffmlp — the fully fused MLP module behind the reference's name (FFMLP, reference ffmlp/ffmlp.py:99-168;
+ffmlp_forward :15-86).  Same constructor, same parameter (`weights`: one flat fp32 vector holding the [out,in] row-major matrices
+back to back, ffmlp.cu:631-634), same initialisation (global seed 42, U(+-sqrt(3/hidden)), ffmlp.py:141-144), output padded to 16
+columns (ffmlp.py:118).  The op is ngp_autograd.FFMLPFn over the tcgen05/TMEM kernels of csrc/ffmlp.cu.
 
-Same constructor, parameter layout (`weights`: one flat fp32 vector of [out,in] row-major matrices,
-ffmlp.cu:631-634), same init (global seed 42 + U(+-sqrt(3/hidden)), ffmlp.py:141-144), output padded to 16
-(ffmlp.py:118).  The reference's batch padding to a multiple of 128 (ffmlp.py:157-159, a cat-copy of the input) is
-internal to it and replaced by in-kernel masking of the ragged last tile.  Underneath: the tcgen05/TMEM kernels of csrc/ffmlp.cu via the
-C-ABI.  The stray `from turtle import ...` of the reference (ffmlp.py:2) is deliberately not reproduced.
+The reference pads the batch to a multiple of 128 with a cat-copy of the input (ffmlp.py:157-159); the kernels here mask the ragged
+last tile instead, so no copy is made and results are identical.  (The stray `from turtle import ...` of ffmlp.py:2 is not reproduced.)
 """
 import math
 
 import torch
 import torch.nn as nn
-from torch.autograd import Function
-from torch.amp import custom_bwd, custom_fwd
 
 import _ngp_b200 as _backend
+from ngp_autograd import ffmlp_forward   # noqa: F401  (re-exported under the reference's name)
 
-
-class _ffmlp_forward(Function):
-    @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.half)
-    def forward(ctx, inputs, weights, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation,
-                inference=False, calc_grad_inputs=False):
-        _backend.require_cuda(inputs, weights)
-        B = inputs.shape[0]
-        inputs = inputs.contiguous()
-        weights = weights.contiguous()
-        if inputs.dtype != torch.half or weights.dtype != torch.half:
-            # outside autocast the reference's CHECK_IS_HALF raises; be explicit about it
-            raise RuntimeError("ffmlp: inputs and weights must be half (run under torch.autocast or cast explicitly)")
-
-        outputs = torch.empty(B, output_dim, device=inputs.device, dtype=inputs.dtype)
-        if not inference:
-            forward_buffer = torch.empty(num_layers, B, hidden_dim, device=inputs.device, dtype=inputs.dtype)
-            _backend.call("ngp_ffmlp_forward", inputs.data_ptr(), weights.data_ptr(), B, input_dim, output_dim,
-                          hidden_dim, num_layers, activation, output_activation, forward_buffer.data_ptr(),
-                          outputs.data_ptr())
-            ctx.save_for_backward(inputs, weights, outputs, forward_buffer)
-            ctx.dims = (input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, calc_grad_inputs)
-        else:
-            _backend.call("ngp_ffmlp_inference", inputs.data_ptr(), weights.data_ptr(), B, input_dim, output_dim,
-                          hidden_dim, num_layers, activation, output_activation, None, outputs.data_ptr())
-        return outputs
-
-    @staticmethod
-    @custom_bwd(device_type='cuda')
-    def backward(ctx, grad):
-        # grad: [B, output_dim]
-        B = grad.shape[0]
-        grad = grad.contiguous()
-        if grad.dtype != torch.half:
-            grad = grad.half()
-        inputs, weights, outputs, forward_buffer = ctx.saved_tensors
-        input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, calc_grad_inputs = ctx.dims
-
-        grad_inputs = torch.empty_like(inputs) if calc_grad_inputs else None
-        grad_weights = torch.empty_like(weights)
-        # the fused dgrad+wgrad kernel keeps dL/d(pre-activation) on chip; only nets deeper than 5 hidden layers
-        # (two-kernel fallback) need the reference's [num_layers, B, hidden] scratch in HBM
-        backward_buffer = (torch.empty(num_layers, B, hidden_dim, device=grad.device, dtype=grad.dtype)
-                           if num_layers + 1 > 6 else None)
-        ws_bytes = _backend.load().ngp_ffmlp_backward_workspace_bytes(B, input_dim, output_dim, hidden_dim, num_layers)
-        workspace = torch.empty(ws_bytes // 4, device=grad.device, dtype=torch.float32)
-
-        _backend.call("ngp_ffmlp_backward", grad.data_ptr(), inputs.data_ptr(), weights.data_ptr(),
-                      forward_buffer.data_ptr(), B, input_dim, output_dim, hidden_dim, num_layers, activation,
-                      output_activation, int(calc_grad_inputs), _backend.ptr(backward_buffer),
-                      _backend.ptr(grad_inputs), grad_weights.data_ptr(), workspace.data_ptr(), ws_bytes)
-
-        if calc_grad_inputs:
-            return grad_inputs, grad_weights, None, None, None, None, None, None, None, None
-        return None, grad_weights, None, None, None, None, None, None, None, None
-
-
-ffmlp_forward = _ffmlp_forward.apply
+ACTIVATION_IDS = {'relu': 0, 'exponential': 1, 'sine': 2, 'sigmoid': 3, 'squareplus': 4, 'softplus': 5}
+ACT_NONE = 6
 
 
 def convert_activation(act):
-    if act == 'relu': return 0
-    elif act == 'exponential': return 1
-    elif act == 'sine': return 2
-    elif act == 'sigmoid': return 3
-    elif act == 'squareplus': return 4
-    elif act == 'softplus': return 5
-    else: return 6
+    """name -> the integer code of ffmlp.h's Activation enum (anything unknown means 'none')."""
+    return ACTIVATION_IDS.get(act, ACT_NONE)
 
 
 class FFMLP(nn.Module):
+    tensorcore_width = 16
+
     def __init__(self, input_dim, output_dim, hidden_dim, num_layers, activation='relu'):
         super().__init__()
-        self.input_dim = input_dim
-        self.output_dim = output_dim
-        self.hidden_dim = hidden_dim
-        self.num_layers = num_layers
+        # the reference's constraints (ffmlp.py:112-115); AssertionError like there
+        assert hidden_dim in (16, 32, 64, 128, 256), f"FFMLP: hidden_dim {hidden_dim} not in (16, 32, 64, 128, 256)"
+        assert input_dim > 0 and input_dim % 16 == 0, f"FFMLP: input_dim {input_dim} must be a positive multiple of 16"
+        assert output_dim <= 16, f"FFMLP: output_dim {output_dim} > 16 is not supported"
+        assert num_layers >= 2, f"FFMLP: num_layers {num_layers} < 2 (at least 3 matmuls)"
+        self.input_dim, self.output_dim, self.hidden_dim, self.num_layers = input_dim, output_dim, hidden_dim, num_layers
         self.activation = convert_activation(activation)
-        self.output_activation = convert_activation('none')  # not supported (reference ffmlp.py:108)
-
-        self.tensorcore_width = 16
-
-        assert hidden_dim in [16, 32, 64, 128, 256], f"FFMLP only support hidden_dim in [16, 32, 64, 128, 256], but got {hidden_dim}"
-        assert input_dim > 0 and input_dim % 16 == 0, f"FFMLP input_dim should be 16 * m (m  > 0), but got {input_dim}"
-        assert output_dim <= 16, f"FFMLP current only supports output dim <= 16, but got {output_dim}"
-        assert num_layers >= 2, f"FFMLP num_layers should be larger than 2 (3 matmuls), but got {num_layers}"
-
-        # pad output
-        self.padded_output_dim = int(math.ceil(output_dim / 16)) * 16
-
-        # parameters (continuous in memory)
+        self.output_activation = ACT_NONE                          # the reference supports none either (ffmlp.py:108)
+        self.padded_output_dim = -(-output_dim // 16) * 16
         self.num_parameters = hidden_dim * (input_dim + hidden_dim * (num_layers - 1) + self.padded_output_dim)
         self.weights = nn.Parameter(torch.zeros(self.num_parameters))
         self.reset_parameters()
-
-        # the reference allocates global split-K streams here (ffmlp.py:126); kept as an ABI no-op
         if torch.cuda.is_available():
-            _backend.load().ngp_ffmlp_allocate_splitk(self.num_layers + 1)
+            # the reference creates process-global split-K streams here (ffmlp.py:126); an ABI no-op in this library
+            _backend.load().ngp_ffmlp_allocate_splitk(num_layers + 1)
 
     def cleanup(self):
         _backend.load().ngp_ffmlp_free_splitk()
 
-    def __repr__(self):
-        return f"FFMLP: input_dim={self.input_dim} output_dim={self.output_dim} hidden_dim={self.hidden_dim} num_layers={self.num_layers} activation={self.activation}"
-
     def reset_parameters(self):
-        torch.manual_seed(42)  # reference behaviour: reseeds the global RNG
-        std = math.sqrt(3 / self.hidden_dim)
-        self.weights.data.uniform_(-std, std)
+        torch.manual_seed(42)      # reference behaviour: every FFMLP construction reseeds the GLOBAL generator
+        bound = math.sqrt(3 / self.hidden_dim)
+        self.weights.data.uniform_(-bound, bound)
+
+    def __repr__(self):
+        return (f"FFMLP: input_dim={self.input_dim} output_dim={self.output_dim} hidden_dim={self.hidden_dim} "
+                f"num_layers={self.num_layers} activation={self.activation}")
 
     def forward(self, inputs):
-        # inputs: [B, input_dim] -> [B, output_dim]
-        B, C = inputs.shape
-        # The reference pads the batch to a multiple of 128 with a torch.cat copy of the whole input (ffmlp.py:157-159).
-        # The tcgen05 kernels mask the ragged last tile themselves, so no copy is made; results are identical.
-        outputs = ffmlp_forward(inputs, self.weights, self.input_dim, self.padded_output_dim, self.hidden_dim,
-                                self.num_layers, self.activation, self.output_activation, not self.training,
-                                inputs.requires_grad)
-
-        # unpad output
-        if B != outputs.shape[0] or self.padded_output_dim != self.output_dim:
-            outputs = outputs[:B, :self.output_dim]
-        return outputs
+        """inputs [B, input_dim] -> [B, output_dim] (half under autocast)"""
+        y = ffmlp_forward(inputs, self.weights, self.input_dim, self.padded_output_dim, self.hidden_dim, self.num_layers,
+                          self.activation, self.output_activation, not self.training, inputs.requires_grad)
+        return y if self.padded_output_dim == self.output_dim else y[:, :self.output_dim]
