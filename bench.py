@@ -253,7 +253,6 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import _ngp_b200 as nb
     import ngp_dp
-    from nerf_step import train_step
     nb.load()
 
     R = args.rays_per_step

@@ -7,7 +7,6 @@ with the same tensor preparation as gridencoder/grid.py:24-90, ffmlp/ffmlp.py:15
 shencoder/sphere_harmonics.py:14-54 and raymarching/raymarching.py:161-291 (including their permute / cat-pad /
 zeros_like copies), and the same caller sequence as nerf/network_ff.py:51-74 + nerf/renderer.py:280-321.
 """
-import numpy as np
 import torch
 from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
