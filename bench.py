@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the steady-state step in a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true", help="GradScaler + torch fused Adam on fp32 .grad (reference trainer sequence) instead of the fused fp16-sink optimizer kernel")
     ap.add_argument("--unfused", action="store_true", help="evaluate the field module by module (network_ff.py call sequence) instead of the fused field kernels")
+    ap.add_argument("--chunks", type=int, default=4, help="row chunks of the fused field (side-stream pipelining of color fwd / table scatter); 1 = off")
+    ap.add_argument("--no-prefetch", action="store_true", help="march each step's rays inside that step instead of one step ahead on a low-priority stream")
+    ap.add_argument("--prefetch-point", default="auto", choices=["auto", "start", "exchange"])
+    ap.add_argument("--long-steps", type=int, default=200, help="extra, longer timed region reported as `long_run` (0 = skip)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c5", "infer"], help="BASELINE.json config: c2 = training step (default; c4 = the same under torchrun), c1 = GridEncoder fwd/bwd 64k points, c3 = fused density inference 4096x1024, c5 = SDF 1M points, infer = full-frame eval render")
     return ap.parse_args()
 
 
@@ -120,20 +125,21 @@ def units_of(name, args):
         B, ind, outd, hid, nl = args[2], args[3], args[4], args[5], args[6]
         params = hid * (ind + hid * (nl - 1) + outd)
         return B, B * 2 * (ind + outd + (nl * hid if name == "ngp_ffmlp_forward" else 0)), 2 * params * B
-    if name == "ngp_ffmlp_backward":
+    if name in ("ngp_ffmlp_backward", "ngp_ffmlp_backward_ex"):
         B, ind, outd, hid, nl = args[4], args[5], args[6], args[7], args[8]
         params = hid * (ind + hid * (nl - 1) + outd)
         return B, B * 2 * (outd + ind + nl * hid + ind), 4 * params * B      # reads dY, X, forward stash; writes dX
     if name == "ngp_field_sigma_forward":
         L, nl, M, train = args[3], args[9], args[10], args[11]
         params = 64 * (2 * L + 64 * (nl - 1) + 16)
-        return M, M * (12 + 16 * L * 8 * 2 + (2 * 2 * L + nl * 128 if train else 0) + 32 + 4), 2 * params * M
+        # 12 B xyz + L*8 corners*2 features*2 B gathers (512 B at L=16) + [feature stash 4L + hidden stash nl*128] + h 32 B + sigma 4 B
+        return M, M * (12 + L * 8 * 2 * 2 + (2 * 2 * L + nl * 128 if train else 0) + 32 + 4), 2 * params * M
     if name == "ngp_field_color_forward":
         nl, M, train = args[3], args[4], args[5]
         params = 64 * (32 + 64 * (nl - 1) + 16)
         return M, M * (12 + 32 + (nl * 128 if train else 0) + 12), 2 * params * M
-    if name == "ngp_field_color_backward":
-        nl, M = args[7], args[8]
+    if name in ("ngp_field_color_backward", "ngp_field_color_backward_ex"):
+        nl, M = (args[7], args[8]) if name == "ngp_field_color_backward" else (args[9], args[10])
         params = 64 * (32 + 64 * (nl - 1) + 16)
         return M, M * (12 + 12 + 4 + 32 + 12 + nl * 128 + 32), 4 * params * M
     if name == "ngp_march_rays_train":
@@ -266,18 +272,20 @@ def main():
     log("inputs ready")
     params = [model.encoder.embeddings, model.sigma_net.weights, model.color_net.weights]
     use_fused_opt = not (args.torch_optimizer or args.unfused)
-    stage = [tuple(torch.empty_like(t) for t in dev_in[0])]   # device staging for the e2e H2D copies
+    # static device staging: rays of the NEXT step (marched one step ahead) and targets of the CURRENT step
+    stage = tuple(torch.empty_like(t) for t in dev_in[0])
+    prefetch = use_fused_opt and not args.no_prefetch
+    fstep = None
     if use_fused_opt:
         from ngp_optim import FusedFieldOptimizer
         fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0)
 
         from nerf_step import FusedTrainStep
-        fstep = FusedTrainStep(model, fopt, R, perturb=True)
+        ppoint = args.prefetch_point if args.prefetch_point != "auto" else ("exchange" if world > 1 else "start")
+        fstep = FusedTrainStep(model, fopt, R, perturb=True, chunks=args.chunks, prefetch_point=ppoint)
 
         def step(ro, rd, tgt):
-            if model.mean_count > 0:
-                # steady state: autograd-free step driver (same kernels; MSE gradient in closed form), graph-capturable
-                return fstep(ro, rd, tgt), None
+            """budget-establishing step (no sample budget yet): autograd through the fused field, same optimizer"""
             with torch.autocast("cuda", dtype=torch.float16):
                 out = model.render_train(ro, rd, perturb=True)
                 loss = ((out["image"] - tgt) ** 2).sum() / (3.0 * R)
@@ -308,33 +316,53 @@ def main():
         model.mean_count = 0
         loss, out = step(*dev_in[c])
         counts.append(int(model.step_counter[(model.local_step - 1) % 16, 0].item()))
-        log(f"budget step {c}: samples={counts[-1]} loss={float(loss):.5f}")
+        log(f"budget step {c}: samples={counts[-1]} loss={float(loss.detach()):.5f}")
     model.mean_count = max(counts)       # no ray is dropped in the timed region (dropping = skipped work)
     samples_per_step_local = float(np.mean(counts))
 
-    # ---- the steady-state step (no host sync inside: device-side sample budget, loss scale and
-    # optimizer) is captured once in a CUDA graph and replayed; inputs are copied into the graph's static buffers ----
-    graph = None
-    graph_loss = None
+    # ---- the steady-state step.  Fused path: FusedTrainStep (no autograd, no host sync, device-side sample budget / loss scale /
+    # optimizer).  Step i consumes the samples marched during step i-1 and marches the rays of step i+1 on a low-priority stream
+    # (`prefetch`), so one call = {march(i+1) || [forward(i), backward(i), exchange(i), optimizer(i)]}.  The whole step runs on a
+    # high-priority stream so that the prefetch only fills idle issue slots.  Two CUDA graphs (even / odd sample slot) are captured
+    # and replayed alternately; inputs are copied into the graphs' static buffers.
+    it_global = [0]          # step index, continued across the warm-up / timed / e2e loops (camera i % N_CAMERAS)
+    hp = torch.cuda.Stream(priority=-1)
+
+    def fused_call(tgt, nro, nrd):
+        if prefetch:
+            return fstep.step_prefetched(tgt, nro, nrd)
+        return fstep(nro, nrd, tgt)
+
+    graphs = None
+    graph_loss = [None, None]
+    if use_fused_opt:
+        # first samples: camera 0 (consumed by the first steady-state step)
+        hp.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(hp):
+            if prefetch:
+                fstep.march(dev_in[0][0], dev_in[0][1])
+            for i in range(4):      # warm the allocator pools / both slots eagerly
+                c, cn = it_global[0] % N_CAMERAS, (it_global[0] + 1) % N_CAMERAS
+                if prefetch:
+                    fused_call(dev_in[c][2], dev_in[cn][0], dev_in[cn][1])
+                else:
+                    fused_call(dev_in[c][2], dev_in[c][0], dev_in[c][1])
+                it_global[0] += 1
+        torch.cuda.current_stream().wait_stream(hp)
+        torch.cuda.synchronize()
     if use_fused_opt and not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for i in range(3):
-                    for dst, src in zip(stage[0], dev_in[i % N_CAMERAS]):
-                        dst.copy_(src)
-                    step(*stage[0])
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                graph_loss, _ = step(*stage[0])
-            torch.cuda.synchronize()
-            log("CUDA graph captured")
+            graphs = []
+            for par in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=hp):
+                    graph_loss[par] = fused_call(stage[2], stage[0], stage[1])
+                graphs.append(g)
+                torch.cuda.synchronize()
+            log("CUDA graphs captured (even / odd sample slot)")
         except Exception as e:
-            log(f"CUDA graph capture failed, running eagerly: {type(e).__name__}: {str(e)[:200]}")
-            graph = None
+            log(f"CUDA graph capture failed, running eagerly: {type(e).__name__}: {str(e)[:300]}")
+            graphs = None
             torch.cuda.synchronize()
 
     # ---- occupancy-grid maintenance: the reference trainer calls update_extra_state every 16 steps
@@ -372,44 +400,70 @@ def main():
     for ev in consumed:
         ev.record()
 
+    def host_triplet(i):
+        """(rays_o, rays_d) of the step whose samples are generated during step i, and the target step i consumes."""
+        c = i % N_CAMERAS
+        cn = (i + 1) % N_CAMERAS if prefetch else c
+        return host_in[cn][0], host_in[cn][1], host_in[c][2]
+
+    def dev_triplet(i):
+        c = i % N_CAMERAS
+        cn = (i + 1) % N_CAMERAS if prefetch else c
+        return dev_in[cn][0], dev_in[cn][1], dev_in[c][2]
+
     def run_loop(n, e2e, eager=False):
         last = None
-        for i in range(n):
-            c = i % N_CAMERAS
-            if graph is not None and not eager:
+        cur = torch.cuda.current_stream()
+        for k in range(n):
+            i = it_global[0]
+            if use_fused_opt:
                 if e2e:
                     # pinned host -> device on a copy stream, one step ahead (double-buffered landing zones), so the PCIe
                     # transfer of step i+1 overlaps the compute of step i; every step's bytes are still copied inside the
                     # timed region
-                    if i == 0:
+                    if k == 0:
                         with torch.cuda.stream(copy_stream):
-                            for dst, src in zip(landing[0], host_in[c]):
+                            copy_stream.wait_event(consumed[i % 2])
+                            for dst, src in zip(landing[i % 2], host_triplet(i)):
                                 dst.copy_(src, non_blocking=True)
-                            copy_done[0].record(copy_stream)
-                    if i + 1 < n:
+                            copy_done[i % 2].record(copy_stream)
+                    if k + 1 < n:
                         with torch.cuda.stream(copy_stream):
                             copy_stream.wait_event(consumed[(i + 1) % 2])
-                            for dst, src in zip(landing[(i + 1) % 2], host_in[(i + 1) % N_CAMERAS]):
+                            for dst, src in zip(landing[(i + 1) % 2], host_triplet(i + 1)):
                                 dst.copy_(src, non_blocking=True)
                             copy_done[(i + 1) % 2].record(copy_stream)
-                    torch.cuda.current_stream().wait_event(copy_done[i % 2])
-                    for dst, src in zip(stage[0], landing[i % 2]):
-                        dst.copy_(src, non_blocking=True)
-                    consumed[i % 2].record()
+                    cur.wait_event(copy_done[i % 2])
+                    src3 = landing[i % 2]
                 else:
-                    for dst, src in zip(stage[0], dev_in[c]):
+                    src3 = dev_triplet(i)
+                if graphs is not None and not eager:
+                    for dst, src in zip(stage, src3):
                         dst.copy_(src, non_blocking=True)
-                graph.replay()
-                if e2e:
-                    last = graph_loss.item()                # device -> host read of the step's result
+                    if e2e:
+                        consumed[i % 2].record()
+                    graphs[i % 2].replay()
+                    if e2e:
+                        last = graph_loss[i % 2].item()                # device -> host read of the step's result
+                else:
+                    fstep.set_slot(i)
+                    hp.wait_stream(cur)
+                    with torch.cuda.stream(hp):
+                        loss = fused_call(src3[2], src3[0], src3[1])
+                    cur.wait_stream(hp)
+                    if e2e:
+                        consumed[i % 2].record()
+                        last = loss.item()
             elif e2e:
-                for dst, src in zip(stage[0], host_in[c]):
+                c = i % N_CAMERAS
+                for dst, src in zip(stage, host_in[c]):
                     dst.copy_(src, non_blocking=True)
-                loss, _ = step(*stage[0])
+                loss, _ = step(*stage)
                 last = loss.item()            # device -> host read of the step's result
             else:
-                loss, _ = step(*dev_in[c])
-            if maint is not None and (i + 1) % 16 == 0:
+                loss, _ = step(*dev_in[i % N_CAMERAS])
+            it_global[0] += 1
+            if maint is not None and (k + 1) % 16 == 0:
                 maint()
         return last
 
@@ -434,21 +488,36 @@ def main():
         return float(ms.item()), launches, rec
 
     W = max(args.warmup, 3)
-    run_loop(W, False)
+    run_loop(W, False)            # (step index i <-> sample slot i % 2 <-> graph i % 2 throughout)
     torch.cuda.synchronize()
     log("warm-up done")
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
     t0 = sampler.mark()
-    if graph is not None:
-        ms_total, _, _ = timed(args.steps, False)                                      # graph replay: the headline timing
+    long_run = None
+    if use_fused_opt:
+        ms_total, _, _ = timed(args.steps, False)                                      # the headline timing (graph replay unless --no-graph)
         t1 = sampler.mark()
+        if args.long_steps > args.steps:
+            ms_long, _, _ = timed(args.long_steps, False)
+            long_run = {"steps": args.long_steps, "ms_per_step": ms_long / args.long_steps, "value": R * args.long_steps / (ms_long * 1e-3),
+                        "timed_region_s": ms_long * 1e-3}
+            t1 = sampler.mark()
         clocks = sampler.stop(t0, t1)
-        # per-kernel CUDA-event durations need individual launches: the same K steps once more, eagerly
-        run_loop(2, False, eager=True)      # re-warm the eager allocator pool (the graph owns its own)
+        # per-kernel CUDA-event durations need individual, non-overlapping launches: the same K steps once more, eagerly,
+        # with the pipelining switched off (chunks = 1, march inside the step)
+        saved = (fstep.chunks, prefetch)
+        torch.cuda.synchronize()
+        fstep.chunks, prefetch = 1, False
+        run_loop(2, False, eager=True)      # re-warm the eager allocator pool (the graphs own theirs)
         ms_eager, launches, rec = timed(args.steps, False, profile=True, eager=True)
-        log(f"eager (per-kernel event pass): {ms_eager / args.steps:.2f} ms/step")
+        log(f"eager unpipelined (per-kernel event pass): {ms_eager / args.steps:.2f} ms/step")
+        fstep.chunks, prefetch = saved
+        if prefetch:
+            fstep.set_slot(it_global[0])
+            fstep.march(*dev_triplet(it_global[0] - 1)[:2])     # refill the current slot for the loops that follow
+            torch.cuda.synchronize()
     else:
         ms_total, launches, rec = timed(args.steps, False, profile=True)
         ms_eager = ms_total
@@ -514,7 +583,11 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "kernel_time_share": kern_ms / ms_eager, "kernels": breakdown,
-            "cuda_graph": graph is not None, "ms_per_step_eager": ms_eager / args.steps}
+            "cuda_graph": graphs is not None, "ms_per_step_eager_unpipelined": ms_eager / args.steps,
+            "pipelining": {"field_chunks": args.chunks if use_fused_opt else 1, "march_prefetch": bool(prefetch),
+                           "prefetch_point": (fstep.prefetch_point if fstep is not None else None),
+                           "note": "per-kernel figures (`kernels`, `roofline`) come from an eager pass with the pipelining switched off, so that each launch is timed alone; the headline is the pipelined, graph-replayed step"},
+            "long_run": long_run, "timed_region_s": ms_total * 1e-3}
 
     # side arms run in child processes with hard timeouts: a reported baseline must never cost the bench line
     def child(cmd, timeout):

@@ -107,6 +107,19 @@ int ngp_ffmlp_backward(const void* grad, const void* inputs, const void* weights
                        uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
                        void* backward_buffer, void* grad_inputs, void* grad_weights,
                        void* workspace, size_t workspace_bytes, ngp_stream_t stream);
+/* Pipelined variant of ngp_ffmlp_backward (extension): a caller that splits one batch into row chunks — to overlap this kernel
+ * with the hash-grid scatter of the previous chunk on another stream — accumulates all chunks into ONE fp32 workspace. */
+#define NGP_WGRAD_ACCUMULATE  1u  /* the workspace already holds partial sums: do not zero it                              */
+#define NGP_WGRAD_NO_FINALIZE 2u  /* leave the fp32 sums in the workspace (grad_weights may be NULL)                        */
+int ngp_ffmlp_backward_ex(const void* grad, const void* inputs, const void* weights,
+                          const void* forward_buffer, uint32_t B, uint32_t input_dim,
+                          uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                          uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
+                          void* backward_buffer, void* grad_inputs, void* grad_weights,
+                          void* workspace, size_t workspace_bytes, uint32_t flags, ngp_stream_t stream);
+/* zero_first != 0: clear the n_params-float workspace (start of a chunked pass); else convert it to fp16 grad_weights. */
+int ngp_ffmlp_wgrad_finalize(void* workspace, void* grad_weights, uint32_t n_params, int zero_first,
+                             ngp_stream_t stream);
 /* ffmlp.h:13-14 — the reference (re)creates global side streams here; this build needs none. */
 int ngp_ffmlp_allocate_splitk(size_t size);
 int ngp_ffmlp_free_splitk(void);
@@ -157,6 +170,12 @@ int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32
 /* dirs [M,3] f32, h_sigma [M,16] fp16 -> rgb_out [M,3] f32 = sigmoid(color_net([SH4(dir) | h_sigma[:,1:] | 0])[:, :3]) */
 int ngp_field_color_forward(const float* dirs, const void* h_sigma, const void* weights, uint32_t num_layers,
                             uint32_t M, int train, void* forward_buffer, float* rgb_out, ngp_stream_t stream);
+/* General form: pad (nullable) [M] fp16 = last input column of the color net (NULL = the zero pad of network_ff.py:67);
+ * rgb_out NULL -> plain FFMLP output (pre-sigmoid) into h_out [M,16] fp16 instead (what ffmlp.FFMLP returns: the drop-in modules
+ * use this when they recognise the SHEncoder -> cat -> FFMLP pattern). */
+int ngp_field_color_forward_ex(const float* dirs, const void* h_sigma, const void* pad, const void* weights,
+                               uint32_t num_layers, uint32_t M, int train, void* forward_buffer, float* rgb_out,
+                               void* h_out, ngp_stream_t stream);
 /* color-net backward incl. sigmoid / cat / trunc_exp gradients: writes dys_out [M,16] fp16 = dL/d(sigma-net output)
  * and grad_weights (color net).  The sigma net then uses ngp_ffmlp_backward(grad = dys_out, inputs = feat). */
 int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* d_sigma, const void* h_sigma,
@@ -164,9 +183,20 @@ int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* 
                              uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
                              size_t workspace_bytes, ngp_stream_t stream);
 
+/* General form: the output gradient either as (d_rgb, rgb) [sigmoid gradient formed in the kernel] or as grad_h [M,3] fp16 =
+ * dL/d(network output); d_sigma nullable (column 0 of dys_out is then 0: the caller's autograd handles trunc_exp); pad as in the
+ * forward; flags = NGP_WGRAD_* as ngp_ffmlp_backward_ex. */
+int ngp_field_color_backward_ex(const float* d_rgb, const float* rgb, const void* grad_h, const float* d_sigma,
+                                const void* h_sigma, const float* dirs, const void* pad, const void* weights,
+                                const void* forward_buffer, uint32_t num_layers, uint32_t M, void* dys_out,
+                                void* grad_weights, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                ngp_stream_t stream);
+
 /* ---- fused optimizer step (replaces GradScaler.unscale_/inf-check + torch.optim.Adam +
  * the per-forward fp32->fp16 table cast + gradient zeroing of nerf/utils.py:866-868, main_nerf.py:132, grid.py:43-44).
- * `state` = 4 device words {float scale, int growth_tracker, int found_inf, int step}; no host synchronisation. ---- */
+ * `state` = 8 device words {float scale, int growth_tracker, int found_inf, int step, float lr_scale, 3 reserved}; the step size
+ * is lr * lr_scale (lr_scale lives on the device so that a schedule can change it between replays of a captured CUDA graph);
+ * no host synchronisation. ---- */
 int ngp_optim_check_finite(const void* grads, int dtype, uint64_t n, void* state, ngp_stream_t stream);
 int ngp_optim_adam_step(float* params, float* exp_avg, float* exp_avg_sq, void* grads, int dtype, void* shadow_f16,
                         uint64_t n, float lr, float beta1, float beta2, float eps, const void* state, int zero_grad,

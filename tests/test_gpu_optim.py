@@ -14,7 +14,8 @@ def test_adam_matches_torch_and_skips_on_inf(n):
     p0 = torch.randn(n, generator=gen(1)).cuda()
     p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
     shadow = torch.empty(n, dtype=torch.half, device="cuda")
-    state = torch.zeros(4, dtype=torch.int32, device="cuda"); state[0:1].view(torch.float32).fill_(1024.0)
+    state = torch.zeros(8, dtype=torch.int32, device="cuda"); state[0:1].view(torch.float32).fill_(1024.0)
+    state[4:5].view(torch.float32).fill_(1.0)          # lr_scale
     ref = torch.nn.Parameter(p0.clone())
     opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
     for it in range(5):

@@ -98,6 +98,34 @@ def test_march_multi_cascade_bitexact_vs_oracle():
         np.testing.assert_array_equal(gather_segments(deltas.cpu().numpy(), r), gather_segments(odl, orays))
 
 
+def test_march_small_max_steps_clamp_order():
+    """max_steps < H / 2^(C-1) makes dt_min > dt_max; the reference's clamp fminf(max, fmaxf(min, x)) then returns dt_max.  With
+    dt_gamma == 0 the marcher's constant step must be that value in the probe loop AND in the emitted deltas (raymarching.cu:345-398)."""
+    from oracle import oracle as O
+    import _ngp_b200 as nb
+    N, max_steps = 2048, 64
+    rays_o, rays_d, bitfield, grid, noises = _scene(N)
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), aabb, 0.2)
+    M = N * 128
+    ox, od_, odl, orays, ocnt = O.march_rays_train(rays_o.numpy(), rays_d.numpy(), bitfield.numpy(), 1.0, 0.0, max_steps, 1, 128, M,
+                                                   nears, fars, noises.numpy())
+    xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
+    rays = torch.zeros(N, 3, dtype=torch.int32, device="cuda"); counter = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ro, rd, bf = rays_o.cuda(), rays_d.cuda(), bitfield.cuda()
+    nd, fd, nz = torch.from_numpy(nears).cuda(), torch.from_numpy(fars).cuda(), noises.cuda()
+    nb.call("ngp_march_rays_train", ro.data_ptr(), rd.data_ptr(), bf.data_ptr(), 1.0, 0.0, max_steps, N, 1, 128, M,
+            nd.data_ptr(), fd.data_ptr(), xyzs.data_ptr(), dirs.data_ptr(), deltas.data_ptr(), rays.data_ptr(),
+            counter.data_ptr(), nz.data_ptr())
+    assert counter.cpu().tolist() == ocnt.tolist() and ocnt[0] > 0
+    r = rays.cpu().numpy()
+    np.testing.assert_array_equal(canon_rays(r)[:, [0, 2]], canon_rays(orays)[:, [0, 2]])
+    np.testing.assert_array_equal(gather_segments(xyzs.cpu().numpy(), r), gather_segments(ox, orays))
+    np.testing.assert_array_equal(gather_segments(deltas.cpu().numpy(), r), gather_segments(odl, orays))
+    dt_max = np.float32(2 * 1.7320508075688772) * np.float32(1.0) / np.float32(128)
+    assert np.all(gather_segments(deltas.cpu().numpy(), r)[:, 0] == dt_max)
+
+
 def test_march_rays_train_overflow_and_wrapper():
     """M smaller than the total: dropped rays keep (id, offset, count) but write nothing; wrapper shape rules."""
     import raymarching

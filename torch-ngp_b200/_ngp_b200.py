@@ -26,11 +26,15 @@ _SIGNATURES = {
     "ngp_ffmlp_forward": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "ngp_ffmlp_inference": [_vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp],
     "ngp_ffmlp_backward": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _sz, _vp],
+    "ngp_ffmlp_backward_ex": [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _sz, _u32, _vp],
+    "ngp_ffmlp_wgrad_finalize": [_vp, _vp, _u32, _i32, _vp],
     "ngp_ffmlp_allocate_splitk": [_sz],
     "ngp_ffmlp_free_splitk": [],
     "ngp_field_sigma_forward": [_vp, _vp, _vp, _u32, _f32, _u32, _u32, _i32, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp],
     "ngp_field_color_forward": [_vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp],
     "ngp_field_color_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp],
+    "ngp_field_color_forward_ex": [_vp, _vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp],
+    "ngp_field_color_backward_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _u32, _vp],
     "ngp_debug_umma": [_vp, _vp, _vp, _i32, _vp],
     "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
     "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],

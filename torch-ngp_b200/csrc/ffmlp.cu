@@ -60,13 +60,15 @@ struct FieldArgs {
     // IN_SHGEO (and the color backward)
     const float* dirs;       // [M,3]
     const __half* h_sigma;   // [M,16]
+    const __half* pad;       // [M] last input column of the color net (nullable = zeros, network_ff.py:67)
     // outputs
     float* sigma_out;        // [M]
     float* rgb_out;          // [M,3]
     // color backward
     const float* d_rgb;      // [M,3]
     const float* rgb;        // [M,3] (forward output)
-    const float* d_sigma;    // [M]
+    const float* d_sigma;    // [M] (nullable: column 0 of dys_out is then 0 — trunc_exp handled by the caller)
+    const __half* grad_h;    // [M,3] dL/d(color-net output) given directly (then d_rgb / rgb are unused)
     __half* dys_out;         // [M,16] dL/d(sigma-net output)
 };
 
@@ -93,7 +95,7 @@ __device__ __forceinline__ void sh4_eval(float x, float y, float z, float out[16
 // color-net input row [SH4 | geo(15) | 0] -> 4 x 16-byte chunks of the swizzled tile row `r`
 // SH(dir) | geo | pad row of the color net's input tile from values already in registers
 __device__ __forceinline__ void write_shgeo_row_regs(uint32_t tile_addr, uint32_t r, bool ok, float dx, float dy, float dz,
-                                                     const uint4 h0, const uint4 h1) {
+                                                     const uint4 h0, const uint4 h1, const uint32_t pad_bits = 0u) {
     uint4 c[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (ok) {
         float sh[16];
@@ -107,7 +109,7 @@ __device__ __forceinline__ void write_shgeo_row_regs(uint32_t tile_addr, uint32_
         const uint32_t w[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
         uint32_t g[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = (w[i] >> 16) | ((i < 7 ? w[i + 1] : 0u) << 16);
+        for (int i = 0; i < 8; ++i) g[i] = (w[i] >> 16) | ((i < 7 ? w[i + 1] : pad_bits) << 16);
         c[2] = make_uint4(g[0], g[1], g[2], g[3]);
         c[3] = make_uint4(g[4], g[5], g[6], g[7]);
     }
@@ -251,6 +253,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
     // IN_SHGEO: likewise the direction and the sigma-net output row of the next tile
     float nx_d[3] = {0.f, 0.f, 0.f};
     uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
+    uint32_t nx_pad = 0;
     auto preload_shgeo = [&](uint32_t t) {
         if constexpr (IN_MODE == IN_SHGEO) {
             const size_t rw = (size_t)t * TILE_M + tid;
@@ -259,6 +262,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
                 for (int d = 0; d < 3; ++d) nx_d[d] = __ldg(fa.dirs + rw * 3 + d);
                 nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
                 nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
+                if (fa.pad) nx_pad = __ldg(reinterpret_cast<const unsigned short*>(fa.pad) + rw);
             }
         }
     };
@@ -277,8 +281,9 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
         else if constexpr (IN_MODE == IN_SHGEO) {
             const float cd0 = nx_d[0], cd1 = nx_d[1], cd2 = nx_d[2];
             const uint4 ch0 = nx_h0, ch1 = nx_h1;
+            const uint32_t cpad = nx_pad;
             preload_shgeo(tile + gridDim.x);
-            write_shgeo_row_regs(a_addr, tid, row_ok, cd0, cd1, cd2, ch0, ch1);
+            write_shgeo_row_regs(a_addr, tid, row_ok, cd0, cd1, cd2, ch0, ch1, cpad);
         }
         else load_tile_rowmajor(a_addr, inputs + row0 * in_dim, TILE_M, in_dim, tid, 128, rows_valid);
 
@@ -567,19 +572,27 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
     // one tile ahead into registers, so no round waits on a dependent global load
     float nx_y[3] = {0.f, 0.f, 0.f}, nx_g[3] = {0.f, 0.f, 0.f}, nx_dir[3] = {0.f, 0.f, 0.f}, nx_dsig = 0.f;
     uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
+    uint32_t nx_pad = 0;
     auto preload_rows = [&](uint32_t t) {
         if constexpr (FIELD_COLOR) {
             const size_t rw = (size_t)t * TILE_M + tid;
             if (t < ntiles && rw < (size_t)B) {
+                if (fa.grad_h) {           // dL/dh given directly (drop-in FFMLP path: the caller's autograd ran the sigmoid backward)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    nx_y[c] = __ldg(fa.rgb + rw * 3 + c);
-                    nx_g[c] = __ldg(fa.d_rgb + rw * 3 + c);
-                    nx_dir[c] = __ldg(fa.dirs + rw * 3 + c);
+                    for (int c = 0; c < 3; ++c) nx_g[c] = __half2float(__ldg(fa.grad_h + rw * 3 + c));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        nx_y[c] = __ldg(fa.rgb + rw * 3 + c);
+                        nx_g[c] = __ldg(fa.d_rgb + rw * 3 + c);
+                    }
                 }
-                nx_dsig = __ldg(fa.d_sigma + rw);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nx_dir[c] = __ldg(fa.dirs + rw * 3 + c);
+                if (fa.d_sigma) nx_dsig = __ldg(fa.d_sigma + rw);
                 nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
                 nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
+                if (fa.pad) nx_pad = __ldg(reinterpret_cast<const unsigned short*>(fa.pad) + rw);
             }
         }
     };
@@ -606,6 +619,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
         float cur_dir[3] = {nx_dir[0], nx_dir[1], nx_dir[2]};
         const float cur_dsig = nx_dsig;
         const uint4 cur_h0 = nx_h0, cur_h1 = nx_h1;
+        const uint32_t cur_pad = nx_pad;
         // dL/dy -> G1 (K-major A of round 0 and, zero-padded to 64 columns, MN-major operand of the output-layer wgrad)
         if constexpr (FIELD_COLOR) {
             // dL/dh = half(d_rgb) * y (1 - y), y = rgb (already fp16-representable); columns 3..63 are zero
@@ -614,6 +628,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 float dh[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
+                    if (fa.grad_h) { dh[c] = nx_g[c]; continue; }
                     const float y = nx_y[c];
                     const float g = __half2float(__float2half_rn(nx_g[c]));
                     dh[c] = g * (y * (1.0f - y));
@@ -716,7 +731,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 tmem_ld_wait();
                 if (row_ok) {
                     const float h0 = __low2float(*reinterpret_cast<const __half2*>(&cur_h0.x));
-                    const float g0 = cur_dsig * expf(fminf(fmaxf(h0, -15.f), 15.f));
+                    const float g0 = fa.d_sigma ? cur_dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) : 0.f;
                     uint32_t p[8];
                     p[0] = pack_h2(g0, __uint_as_float(v[0]));
 #pragma unroll
@@ -749,7 +764,7 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
             const uint32_t xq = f_addr[(n_hidden + 1) & 1u];
             if constexpr (FIELD_COLOR) {
                 // (staging these rows earlier, inside the input-gradient round, measured slower: 1.47 vs 1.35 ms)
-                write_shgeo_row_regs(xq, tid, row_ok, cur_dir[0], cur_dir[1], cur_dir[2], cur_h0, cur_h1);
+                write_shgeo_row_regs(xq, tid, row_ok, cur_dir[0], cur_dir[1], cur_dir[2], cur_h0, cur_h1, cur_pad);
                 zero_tile_cols(xq, TILE_M, in_dim >> 3, tid, 128);
             } else if (grad_inputs) {
                 cp_async_wait_all();            // X was staged (cp.async) during the input-gradient round
@@ -1063,11 +1078,14 @@ extern "C" size_t ngp_ffmlp_backward_workspace_bytes(uint32_t B, uint32_t input_
 }
 
 // backward_buffer may be NULL: the fused kernel then keeps dL/d(pre-activation) on chip only.
-extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const void* weights, const void* forward_buffer,
-                                  uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
-                                  uint32_t num_layers, uint32_t activation, uint32_t output_activation,
-                                  int calc_grad_inputs, void* backward_buffer, void* grad_inputs, void* grad_weights,
-                                  void* workspace, size_t workspace_bytes, ngp_stream_t stream) {
+// flags (pipelined callers split one batch into chunks that accumulate into one fp32 workspace):
+//   NGP_WGRAD_ACCUMULATE  : the workspace already holds partial weight gradients — do not zero it
+//   NGP_WGRAD_NO_FINALIZE : leave the fp32 sums in the workspace (ngp_ffmlp_wgrad_finalize converts them later)
+extern "C" int ngp_ffmlp_backward_ex(const void* grad, const void* inputs, const void* weights, const void* forward_buffer,
+                                     uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                                     uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                                     int calc_grad_inputs, void* backward_buffer, void* grad_inputs, void* grad_weights,
+                                     void* workspace, size_t workspace_bytes, uint32_t flags, ngp_stream_t stream) {
     int rc = check_cfg("ffmlp_backward", B, input_dim, output_dim, hidden_dim, num_layers, output_activation);
     if (rc) return rc;
     const size_t need = ngp_ffmlp_backward_workspace_bytes(B, input_dim, output_dim, hidden_dim, num_layers);
@@ -1075,7 +1093,8 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
     if (calc_grad_inputs && !grad_inputs) return fail(NGP_EINVAL, "ffmlp_backward: grad_inputs is null");
     cudaStream_t st = as_stream(stream);
     const uint32_t n_params = (uint32_t)(need / sizeof(float));
-    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return fail(NGP_ECUDA, "ffmlp_backward: memset failed");
+    if (!(flags & NGP_WGRAD_ACCUMULATE) && cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess)
+        return fail(NGP_ECUDA, "ffmlp_backward: memset failed");
     const uint32_t nmat = num_layers + 1;
     __half* gi = calc_grad_inputs ? (__half*)grad_inputs : nullptr;
     if (B > 0 && nmat <= FUSED_MAX_MATMULS) {
@@ -1118,9 +1137,35 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
         rc = check_launch("ffmlp_backward(wgrad)");
         if (rc) return rc;
     }
+    if (flags & NGP_WGRAD_NO_FINALIZE) return NGP_OK;
+    if (!grad_weights) return fail(NGP_EINVAL, "ffmlp_backward: grad_weights is null");
     k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
     return check_launch("ffmlp_backward(finalize)");
 }
+
+extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const void* weights, const void* forward_buffer,
+                                  uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
+                                  uint32_t num_layers, uint32_t activation, uint32_t output_activation,
+                                  int calc_grad_inputs, void* backward_buffer, void* grad_inputs, void* grad_weights,
+                                  void* workspace, size_t workspace_bytes, ngp_stream_t stream) {
+    return ngp_ffmlp_backward_ex(grad, inputs, weights, forward_buffer, B, input_dim, output_dim, hidden_dim, num_layers, activation,
+                                 output_activation, calc_grad_inputs, backward_buffer, grad_inputs, grad_weights, workspace,
+                                 workspace_bytes, 0u, stream);
+}
+
+// fp32 workspace (layout of `weights`) -> fp16 grad_weights; zero_first != 0 clears the workspace instead (start of a chunked pass)
+extern "C" int ngp_ffmlp_wgrad_finalize(void* workspace, void* grad_weights, uint32_t n_params, int zero_first, ngp_stream_t stream) {
+    if (!workspace) return fail(NGP_EINVAL, "ffmlp_wgrad_finalize: workspace is null");
+    cudaStream_t st = as_stream(stream);
+    if (zero_first) {
+        if (cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)n_params, st) != cudaSuccess) return fail(NGP_ECUDA, "ffmlp_wgrad_finalize: memset failed");
+        return NGP_OK;
+    }
+    if (!grad_weights) return fail(NGP_EINVAL, "ffmlp_wgrad_finalize: grad_weights is null");
+    k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
+    return check_launch("ffmlp_wgrad_finalize");
+}
+
 
 // ---- fused NeRF-field entry points (extensions: the reference has no single op for these; they replace
 // GridEncoder -> FFMLP -> trunc_exp and SHEncoder -> cat -> FFMLP -> sigmoid of nerf/network_ff.py:51-74) -------
@@ -1163,46 +1208,65 @@ extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, 
     return check_launch("field_sigma_forward");
 }
 
-extern "C" int ngp_field_color_forward(const float* dirs, const void* h_sigma, const void* weights, uint32_t num_layers,
-                                       uint32_t M, int train, void* forward_buffer, float* rgb_out, ngp_stream_t stream) {
+// pad (nullable) [M] fp16 = the color net's last input column; h_out (nullable) [M,16] fp16 = pre-sigmoid network output.
+// rgb_out non-null: sigmoid epilogue (fused step); rgb_out null: plain FFMLP output into h_out (drop-in FFMLP path).
+extern "C" int ngp_field_color_forward_ex(const float* dirs, const void* h_sigma, const void* pad, const void* weights,
+                                          uint32_t num_layers, uint32_t M, int train, void* forward_buffer, float* rgb_out,
+                                          void* h_out, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     int rc = check_cfg("field_color_forward", M, 32, OUT_PAD, HID, num_layers, ACT_NONE);
     if (rc) return rc;
     if (train && !forward_buffer) return fail(NGP_EINVAL, "field_color_forward: training needs forward_buffer");
+    if (!rgb_out && !h_out) return fail(NGP_EINVAL, "field_color_forward: no output requested");
     FieldArgs fa{};
-    fa.dirs = dirs; fa.h_sigma = (const __half*)h_sigma; fa.rgb_out = rgb_out;
+    fa.dirs = dirs; fa.h_sigma = (const __half*)h_sigma; fa.rgb_out = rgb_out; fa.pad = (const __half*)pad;
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
     const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 4);
     cudaStream_t st = as_stream(stream);
-    if (train) {
-        rc = set_smem(k_ffmlp_forward<true, ACT_RELU, IN_SHGEO, OUT_RGB>, smem, "field_color_forward");
-        if (rc) return rc;
-        k_ffmlp_forward<true, ACT_RELU, IN_SHGEO, OUT_RGB><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, (__half*)forward_buffer,
-                                                                                 nullptr, M, 32, num_layers, fa);
+#define NGP_LAUNCH_COLOR_FWD(TR, OM, FB, OUT)                                                                                    \
+    do {                                                                                                                         \
+        rc = set_smem(k_ffmlp_forward<TR, ACT_RELU, IN_SHGEO, OM>, smem, "field_color_forward");                                 \
+        if (rc) return rc;                                                                                                       \
+        k_ffmlp_forward<TR, ACT_RELU, IN_SHGEO, OM><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, (__half*)(FB),     \
+                                                                             (__half*)(OUT), M, 32, num_layers, fa);              \
+    } while (0)
+    if (rgb_out) {
+        if (train) NGP_LAUNCH_COLOR_FWD(true, OUT_RGB, forward_buffer, nullptr);
+        else NGP_LAUNCH_COLOR_FWD(false, OUT_RGB, nullptr, nullptr);
     } else {
-        rc = set_smem(k_ffmlp_forward<false, ACT_RELU, IN_SHGEO, OUT_RGB>, smem, "field_color_forward");
-        if (rc) return rc;
-        k_ffmlp_forward<false, ACT_RELU, IN_SHGEO, OUT_RGB><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, nullptr, nullptr, M, 32,
-                                                                                  num_layers, fa);
+        if (train) NGP_LAUNCH_COLOR_FWD(true, OUT_PLAIN, forward_buffer, h_out);
+        else NGP_LAUNCH_COLOR_FWD(false, OUT_PLAIN, nullptr, h_out);
     }
+#undef NGP_LAUNCH_COLOR_FWD
     return check_launch("field_color_forward");
 }
 
-extern "C" int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* d_sigma, const void* h_sigma,
-                                        const float* dirs, const void* weights, const void* forward_buffer,
-                                        uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
-                                        size_t workspace_bytes, ngp_stream_t stream) {
+extern "C" int ngp_field_color_forward(const float* dirs, const void* h_sigma, const void* weights, uint32_t num_layers,
+                                       uint32_t M, int train, void* forward_buffer, float* rgb_out, ngp_stream_t stream) {
+    if (M > 0 && !rgb_out) return fail(NGP_EINVAL, "field_color_forward: rgb_out is null");
+    return ngp_field_color_forward_ex(dirs, h_sigma, nullptr, weights, num_layers, M, train, forward_buffer, rgb_out, nullptr, stream);
+}
+
+// Either (d_rgb, rgb) [fused step: sigmoid gradient formed in the kernel] or grad_h [M,3] fp16 = dL/d(network output) given
+// directly.  d_sigma nullable (column 0 of dys_out is then zero).  pad as in the forward.  flags as ngp_ffmlp_backward_ex.
+extern "C" int ngp_field_color_backward_ex(const float* d_rgb, const float* rgb, const void* grad_h, const float* d_sigma,
+                                           const void* h_sigma, const float* dirs, const void* pad, const void* weights,
+                                           const void* forward_buffer, uint32_t num_layers, uint32_t M, void* dys_out,
+                                           void* grad_weights, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                           ngp_stream_t stream) {
     int rc = check_cfg("field_color_backward", M, 32, OUT_PAD, HID, num_layers, ACT_NONE);
     if (rc) return rc;
     if (num_layers + 1 > FUSED_MAX_MATMULS) return fail(NGP_EUNSUPPORTED, "field_color_backward: num_layers must be <= 5");
+    if (!grad_h && (!d_rgb || !rgb)) return fail(NGP_EINVAL, "field_color_backward: need grad_h or (d_rgb, rgb)");
     const size_t need = ngp_ffmlp_backward_workspace_bytes(M, 32, OUT_PAD, HID, num_layers);
     if (!workspace || workspace_bytes < need) return fail(NGP_EINVAL, "field_color_backward: workspace too small");
     cudaStream_t st = as_stream(stream);
-    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return fail(NGP_ECUDA, "field_color_backward: memset failed");
+    if (!(flags & NGP_WGRAD_ACCUMULATE) && cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess)
+        return fail(NGP_ECUDA, "field_color_backward: memset failed");
     if (M > 0) {
         FieldArgs fa{};
-        fa.d_rgb = d_rgb; fa.rgb = rgb; fa.d_sigma = d_sigma; fa.h_sigma = (const __half*)h_sigma; fa.dirs = dirs;
-        fa.dys_out = (__half*)dys_out;
+        fa.d_rgb = d_rgb; fa.rgb = rgb; fa.grad_h = (const __half*)grad_h; fa.d_sigma = d_sigma; fa.h_sigma = (const __half*)h_sigma;
+        fa.dirs = dirs; fa.pad = (const __half*)pad; fa.dys_out = (__half*)dys_out;
         const uint32_t nslots = 1 + (num_layers - 1) + 1;
         const size_t smem = 1024 + 4 * (size_t)A_TILE_BYTES + (size_t)nslots * W_SLOT_BYTES;
         const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 2);
@@ -1214,9 +1278,20 @@ extern "C" int ngp_field_color_backward(const float* d_rgb, const float* rgb, co
         rc = check_launch("field_color_backward");
         if (rc) return rc;
     }
+    if (flags & NGP_WGRAD_NO_FINALIZE) return NGP_OK;
+    if (!grad_weights) return fail(NGP_EINVAL, "field_color_backward: grad_weights is null");
     const uint32_t n_params = (uint32_t)(need / sizeof(float));
     k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
     return check_launch("field_color_backward(finalize)");
+}
+
+extern "C" int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* d_sigma, const void* h_sigma,
+                                        const float* dirs, const void* weights, const void* forward_buffer,
+                                        uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
+                                        size_t workspace_bytes, ngp_stream_t stream) {
+    if (!d_sigma) return fail(NGP_EINVAL, "field_color_backward: d_sigma is null");
+    return ngp_field_color_backward_ex(d_rgb, rgb, nullptr, d_sigma, h_sigma, dirs, nullptr, weights, forward_buffer, num_layers, M,
+                                       dys_out, grad_weights, workspace, workspace_bytes, 0u, stream);
 }
 
 extern "C" int ngp_ffmlp_allocate_splitk(size_t size) { (void)size; return NGP_OK; }

@@ -16,6 +16,8 @@ struct ScalerState {      // device-resident GradScaler state
     int growth_tracker;   // clean steps since the last change
     int found_inf;        // set by k_check_finite for the current step
     int step;             // number of optimizer steps actually taken (bias correction)
+    float lr_scale;       // multiplies the lr argument (LambdaLR-style schedules without re-capturing a CUDA graph)
+    int reserved[3];
 };
 
 template <typename G>
@@ -47,7 +49,7 @@ __global__ void k_adam_step(float* __restrict__ p, float* __restrict__ m, float*
     const int step = st->step + 1;
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2 = 1.0f - powf(beta2, (float)step);
-    const float step_size = lr / bc1;
+    const float step_size = lr * st->lr_scale / bc1;
     const float rsqrt_bc2 = rsqrtf(bc2);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float gi = gload<G>(g, i) * inv_scale;
@@ -74,7 +76,7 @@ __global__ void k_adam_step_vec4(float4* __restrict__ p, float4* __restrict__ m,
     const int step = st->step + 1;
     const float bc1 = 1.0f - powf(beta1, (float)step);
     const float bc2 = 1.0f - powf(beta2, (float)step);
-    const float step_size = lr / bc1;
+    const float step_size = lr * st->lr_scale / bc1;
     const float rsqrt_bc2 = rsqrtf(bc2);
     const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -115,7 +117,7 @@ __global__ void k_scaler_update(ScalerState* st, float growth, float backoff, in
 
 using namespace ngp;
 
-// state: 4 x 32-bit words {float scale, int growth_tracker, int found_inf, int step} on the device
+// state: 8 x 32-bit words {float scale, int growth_tracker, int found_inf, int step, float lr_scale, reserved x3} on the device
 extern "C" int ngp_optim_check_finite(const void* grads, int dtype, uint64_t n, void* state, ngp_stream_t stream) {
     if (n == 0) return NGP_OK;
     const uint32_t blocks = (uint32_t)((n + 256 * 8 - 1) / (256 * 8));

@@ -41,7 +41,7 @@ __device__ __forceinline__ int mip_from_dt(float dt, float H, float max_cascade)
 // ---- per-ray marching state -----------------------------------------------------------------
 struct RayConst {
     float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
-    float bound, dt_gamma, dt_min, dt_max, rH, H3, fH, fC, Hm1;
+    float bound, dt_gamma, dt_min, dt_max, dt_const, rH, H3, fH, fC, Hm1;
     uint32_t H;
 };
 
@@ -57,6 +57,9 @@ __device__ __forceinline__ void ray_setup(RayConst& r, const float* __restrict__
     const float two_sqrt3 = 2 * 1.7320508075688772f;
     r.dt_min = two_sqrt3 / (float)max_steps;
     r.dt_max = two_sqrt3 * (float)(1 << (C - 1)) / (float)H;
+    // the step when dt_gamma == 0: clamp(0, dt_min, dt_max) = fminf(dt_max, fmaxf(dt_min, 0)) — dt_max when dt_min > dt_max
+    // (max_steps < H / 2^(C-1)), exactly as the reference's clamp evaluates it
+    r.dt_const = clampf(0.0f, r.dt_min, r.dt_max);
 }
 
 // One marching decision at parameter t: returns true if the cell is occupied (a sample is taken
@@ -65,15 +68,15 @@ __device__ __forceinline__ void ray_setup(RayConst& r, const float* __restrict__
 //   * the reference's float->double->float cell index chain, (float)(0.5 * (double)a * (double)H), is one correctly
 //     rounded product of a with the exactly representable constant 0.5*H, i.e. the single FMUL a * (0.5f*H);
 //   * with a single cascade (C == 1) both mip_from_* clamp to level 0: frexp/scalbn/reciprocal drop out;
-//   * with dt_gamma == 0 the step clamp(t*0, dt_min, dt_max) is the constant dt_min (also for t = inf: NaN clamps
-//     to dt_min through fmaxf/fminf), so the empty-space loop is add/compare only.
+//   * with dt_gamma == 0 the step clamp(t*0, dt_min, dt_max) is the constant dt_const = min(dt_max, max(dt_min, 0)) (also for
+//     t = inf: NaN clamps to it through fmaxf/fminf), so the empty-space loop is add/compare only.
 __device__ __forceinline__ bool march_probe(const RayConst& r, const uint8_t* __restrict__ grid, float& t,
                                             float& x, float& y, float& z, float& dt) {
     x = clampf(fmaf(t, r.dx, r.ox), -r.bound, r.bound);
     y = clampf(fmaf(t, r.dy, r.oy), -r.bound, r.bound);
     z = clampf(fmaf(t, r.dz, r.oz), -r.bound, r.bound);
     const bool const_dt = (r.dt_gamma == 0.0f);
-    dt = const_dt ? r.dt_min : clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
+    dt = const_dt ? r.dt_const : clampf(t * r.dt_gamma, r.dt_min, r.dt_max);
 
     int level = 0;
     float mip_bound = fminf(1.0f, r.bound), mip_rbound;
@@ -97,7 +100,7 @@ __device__ __forceinline__ bool march_probe(const RayConst& r, const uint8_t* __
     const float tz = (fmaf(fmaf(fmaf(0.5f, signf1(r.dz), (float)nz + 0.5f) * r.rH, 2.0f, -1.0f), mip_bound, -z)) * r.rdz;
     const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
     if (const_dt) {
-        do { t += r.dt_min; } while (t < tt);
+        do { t += r.dt_const; } while (t < tt);
     } else {
         do { t += clampf(t * r.dt_gamma, r.dt_min, r.dt_max); } while (t < tt);
     }

@@ -4,14 +4,15 @@ gridencoder/grid.py:96-185; grid_encode :24-93): same constructor arguments, att
 checkpoints work unchanged.  The op itself lives in ngp_autograd.GridEncodeFn (CUDA: csrc/grid.cu through the C ABI).
 
 Invisible differences: features are produced directly as [B, levels*level_dim] (no [L,B,C] tensor + permute copy, grid.py:57,75)
-and the fp16 copy of the table used under autocast is cached per parameter version instead of re-cast every forward (grid.py:43-44).
+and, when ngp_optim.FusedFieldOptimizer owns the parameters, the fp16 copy of the table used under autocast is the shadow that
+optimizer's kernel keeps current instead of a per-forward cast (grid.py:43-44); without that owner it is re-cast every forward.
 """
 import numpy as np
 import torch
 import torch.nn as nn
 
 import _ngp_b200 as _backend
-from ngp_autograd import grid_encode, _half_table   # noqa: F401  (re-exported under the reference's names)
+from ngp_autograd import grid_encode, _half_table, sync_half_table   # noqa: F401  (re-exported under the reference's names)
 
 GRID_TYPES = {'hash': 0, 'tiled': 1}
 INTERPOLATIONS = {'linear': 0, 'smoothstep': 1}
@@ -50,9 +51,12 @@ class GridEncoder(nn.Module):
         self.n_params = self.offsets[-1] * level_dim
         self.embeddings = nn.Parameter(torch.empty(int(offsets[-1]), level_dim))
         self.reset_parameters()
+        # load_state_dict copies into .data (no version bump): keep an owner-maintained fp16 shadow in step
+        self.register_load_state_dict_post_hook(lambda module, incompatible: sync_half_table(module.embeddings))
 
     def reset_parameters(self):
         self.embeddings.data.uniform_(-1e-4, 1e-4)
+        sync_half_table(self.embeddings)     # a `.data` write: an owner-maintained fp16 shadow must follow it
 
     def __repr__(self):
         finest = int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))

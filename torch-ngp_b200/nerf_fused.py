@@ -1,11 +1,16 @@
-"""nerf_fused.py — optional fused evaluation of the NeRF field (hash grid -> sigma MLP -> trunc_exp ; SH (+) geo ->
-color MLP -> sigmoid) on top of the fused C-ABI extensions (include/ngp_b200.h, ngp_field_*).
+"""nerf_fused.py — fused evaluation of the NeRF field (hash grid -> sigma MLP -> trunc_exp ; SH (+) geo -> color MLP -> sigmoid) on
+top of the fused C-ABI extensions (include/ngp_b200.h, ngp_field_*).
 
-Same mathematics, parameters and rounding points as the module-by-module path of nerf/network_ff.py:51-74 (reference)
-— encoder features bit-identical, MLP outputs identical (same kernels), sigma/rgb within 1 ulp of torch.exp /
-torch.sigmoid — but the encoder output feeds the tensor-core MLP from shared memory, SH + concat + casts happen in
-the color kernel's input staging, and the backward runs sigmoid/cat/trunc_exp gradients inside the MLP backward.
-A caller opts in with one line:   sigma, rgb = fused_field(self.encoder, self.sigma_net, self.color_net, x, d, self.bound)
+Same mathematics, parameters and rounding points as the module-by-module path of nerf/network_ff.py:51-74 (reference) — encoder
+features bit-identical, MLP outputs identical (same kernels), sigma/rgb within 1 ulp of torch.exp / torch.sigmoid — but the encoder
+output feeds the tensor-core MLP from shared memory, SH + concat + casts happen in the color kernel's input staging, and the backward
+runs sigmoid/cat/trunc_exp gradients inside the MLP backward.
+
+Pipelining: the batch can be split into row chunks.  The forward then runs the color net of chunk k (HBM-write bound) on a side stream
+while the gather-bound encoder+sigma kernel works on chunk k+1; the backward runs the hash-table scatter of chunk k (bound by the
+SM's reduction-issue rate, no shared memory) on the side stream underneath the latency-bound tensor-core MLP backward kernels of
+chunk k+1.  Chunks accumulate their weight gradients into one fp32 workspace (NGP_WGRAD_* flags); the table gradient is a
+scatter-add, so chunk order does not matter.
 """
 import numpy as np
 import torch
@@ -13,11 +18,27 @@ from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
 import _ngp_b200 as _backend
-from gridencoder.grid import _half_table
+from ngp_autograd import _half_table
+
+WGRAD_ACCUMULATE, WGRAD_NO_FINALIZE = 1, 2
+DEFAULT_CHUNKS = 1          # autograd path (fused_field); the step driver passes its own chunk count
 
 
-def field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg):
-    """Raw (autograd-free) fused field evaluation.  Returns sigma [M] f32, rgb [M,3] f32 and the backward stash (or None)."""
+def chunk_ranges(M, chunks):
+    """Row ranges [(r0, rows)] of `chunks` near-equal pieces whose starts are multiples of the 128-row MLP tile."""
+    chunks = max(1, min(int(chunks), (M + 127) // 128))
+    per = ((M + chunks - 1) // chunks + 127) // 128 * 128
+    out = []
+    r0 = 0
+    while r0 < M:
+        out.append((r0, min(per, M - r0)))
+        r0 += per
+    return out
+
+
+def field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg, chunks=1, side=None):
+    """Raw (autograd-free) fused field evaluation.  Returns sigma [M] f32, rgb [M,3] f32 and the backward stash (or None).
+    chunks > 1 with a side stream pipelines color(k) under sigma(k+1); the caller's stream has joined the side stream on return."""
     bound, pls, H, gridtype, align_corners, nl_s, nl_c, training = cfg
     _backend.require_cuda(xyzs, dirs, embeddings, sigma_w, color_w)
     x01 = ((xyzs.float() + bound) / (2 * bound)).contiguous()       # GridEncoder.forward's affine map (grid.py:149)
@@ -32,53 +53,86 @@ def field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg):
     h = torch.empty(M, 16, dtype=torch.half, device=dev)
     sigma = torch.empty(M, dtype=torch.float32, device=dev)
     rgb = torch.empty(M, 3, dtype=torch.float32, device=dev)
-    feat = fb_s = fb_c = None
-    if training:
-        feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev)
-        fb_s = torch.empty(nl_s, M, 64, dtype=torch.half, device=dev)
-        fb_c = torch.empty(nl_c, M, 64, dtype=torch.half, device=dev)
-    _backend.call("ngp_field_sigma_forward", x01.data_ptr(), table.data_ptr(), offsets.data_ptr(), L, S, int(H),
-                  gridtype, int(align_corners), ws.data_ptr(), nl_s, M, int(training), _backend.ptr(feat),
-                  _backend.ptr(fb_s), h.data_ptr(), sigma.data_ptr())
-    _backend.call("ngp_field_color_forward", dirs.data_ptr(), h.data_ptr(), wc.data_ptr(), nl_c, M, int(training),
-                  _backend.ptr(fb_c), rgb.data_ptr())
+    ranges = chunk_ranges(M, chunks) if M > 0 else []
+    feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev) if training else None
+    fb_s = [torch.empty(nl_s, rows, 64, dtype=torch.half, device=dev) for _, rows in ranges] if training else []
+    fb_c = [torch.empty(nl_c, rows, 64, dtype=torch.half, device=dev) for _, rows in ranges] if training else []
+    main = torch.cuda.current_stream()
+    piped = side is not None and len(ranges) > 1
+    if piped:
+        side.wait_stream(main)
+    for k, (r0, rows) in enumerate(ranges):
+        _backend.call("ngp_field_sigma_forward", x01.data_ptr() + 12 * r0, table.data_ptr(), offsets.data_ptr(), L, S, int(H),
+                      gridtype, int(align_corners), ws.data_ptr(), nl_s, rows, int(training),
+                      feat.data_ptr() + 4 * L * r0 if training else None, fb_s[k].data_ptr() if training else None,
+                      h.data_ptr() + 32 * r0, sigma.data_ptr() + 4 * r0)
+        if piped:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        with torch.cuda.stream(side if piped else main):
+            _backend.call("ngp_field_color_forward", dirs.data_ptr() + 12 * r0, h.data_ptr() + 32 * r0, wc.data_ptr(), nl_c, rows,
+                          int(training), fb_c[k].data_ptr() if training else None, rgb.data_ptr() + 12 * r0)
+    if piped:
+        main.wait_stream(side)
     stash = None
     if training:
-        stash = dict(tensors=(x01, dirs, offsets, ws, wc, feat, fb_s, fb_c, h, rgb),
-                     cfg=(L, S, int(H), gridtype, int(align_corners), nl_s, nl_c, M, tuple(table.shape)),
+        stash = dict(tensors=(x01, dirs, offsets, ws, wc, feat, h, rgb, *fb_s, *fb_c),
+                     cfg=(L, S, int(H), gridtype, int(align_corners), nl_s, nl_c, M, tuple(table.shape), tuple(ranges)),
                      # optional fp16 gradient sinks installed by ngp_optim.FusedFieldOptimizer (bypass fp32 .grad accumulation)
                      sinks=tuple(getattr(p, "_ngp_grad_sink", None) for p in (embeddings, sigma_w, color_w)))
     return sigma, rgb, stash
 
 
-def field_backward(tensors, cfg, sinks, d_sigma, d_rgb):
-    """Raw backward of field_forward: returns (g_table, gw_sigma, gw_color) — the sinks themselves when installed."""
-    x01, dirs, offsets, ws, wc, feat, fb_s, fb_c, h, rgb = tensors
-    L, S, H, gridtype, align_corners, nl_s, nl_c, M, table_shape = cfg
+def field_backward(tensors, cfg, sinks, d_sigma, d_rgb, side=None):
+    """Raw backward of field_forward: returns (g_table, gw_sigma, gw_color) — the sinks themselves when installed.
+    With a side stream and more than one chunk the table scatter of chunk k runs under the MLP backward kernels of chunk k+1."""
+    L, S, H, gridtype, align_corners, nl_s, nl_c, M, table_shape, ranges = cfg
+    x01, dirs, offsets, ws, wc, feat, h, rgb = tensors[:8]
+    nck = len(ranges)
+    fb_s, fb_c = tensors[8:8 + nck], tensors[8 + nck:8 + 2 * nck]
     dev = x01.device
     d_sigma = d_sigma.float().contiguous()
     d_rgb = d_rgb.float().contiguous()
     lib = _backend.load()
     sink_t, sink_s, sink_c = sinks
-    # color net (+ sigmoid, cat, trunc_exp gradients) -> dL/d(sigma-net output)
-    dys = torch.empty(M, 16, dtype=torch.half, device=dev)
     gw_c = sink_c if sink_c is not None else torch.empty_like(wc)
-    nb_c = lib.ngp_ffmlp_backward_workspace_bytes(M, 32, 16, 64, nl_c)
-    wk_c = torch.empty(nb_c // 4, dtype=torch.float32, device=dev)
-    _backend.call("ngp_field_color_backward", d_rgb.data_ptr(), rgb.data_ptr(), d_sigma.data_ptr(), h.data_ptr(),
-                  dirs.data_ptr(), wc.data_ptr(), fb_c.data_ptr(), nl_c, M, dys.data_ptr(), gw_c.data_ptr(),
-                  wk_c.data_ptr(), nb_c)
-    # sigma net -> dL/d(features)
-    d_feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev)
     gw_s = sink_s if sink_s is not None else torch.empty_like(ws)
-    nb_s = lib.ngp_ffmlp_backward_workspace_bytes(M, 2 * L, 16, 64, nl_s)
-    wk_s = torch.empty(nb_s // 4, dtype=torch.float32, device=dev)
-    _backend.call("ngp_ffmlp_backward", dys.data_ptr(), feat.data_ptr(), ws.data_ptr(), fb_s.data_ptr(), M, 2 * L, 16, 64,
-                  nl_s, 0, 6, 1, None, d_feat.data_ptr(), gw_s.data_ptr(), wk_s.data_ptr(), nb_s)
-    # hash-table scatter-add (a sink is kept zeroed by the optimizer kernel; otherwise a fresh zero table as in grid.py:77)
+    # a sink is kept zeroed by the optimizer kernel; otherwise a fresh zero table as in grid.py:77
     g_table = sink_t if sink_t is not None else torch.zeros(table_shape, dtype=torch.half, device=dev)
-    _backend.call("ngp_grid_encode_backward", d_feat.data_ptr(), x01.data_ptr(), None, offsets.data_ptr(),
-                  g_table.data_ptr(), M, 3, 2, L, S, H, None, None, gridtype, align_corners, 0, 1, 0)
+    nb_c = lib.ngp_ffmlp_backward_workspace_bytes(M, 32, 16, 64, nl_c)
+    nb_s = lib.ngp_ffmlp_backward_workspace_bytes(M, 2 * L, 16, 64, nl_s)
+    wk_c = torch.empty(nb_c // 4, dtype=torch.float32, device=dev)
+    wk_s = torch.empty(nb_s // 4, dtype=torch.float32, device=dev)
+    dys = torch.empty(M, 16, dtype=torch.half, device=dev)          # dL/d(sigma-net output)
+    d_feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev)    # dL/d(encoder features)
+    main = torch.cuda.current_stream()
+    piped = side is not None and nck > 1
+    if piped:
+        side.wait_stream(main)
+    _backend.call("ngp_ffmlp_wgrad_finalize", wk_c.data_ptr(), None, nb_c // 4, 1)
+    _backend.call("ngp_ffmlp_wgrad_finalize", wk_s.data_ptr(), None, nb_s // 4, 1)
+    flags = WGRAD_ACCUMULATE | WGRAD_NO_FINALIZE
+    for k, (r0, rows) in enumerate(ranges):
+        # color net (+ sigmoid, cat, trunc_exp gradients) -> dL/d(sigma-net output)
+        _backend.call("ngp_field_color_backward_ex", d_rgb.data_ptr() + 12 * r0, rgb.data_ptr() + 12 * r0, None,
+                      d_sigma.data_ptr() + 4 * r0, h.data_ptr() + 32 * r0, dirs.data_ptr() + 12 * r0, None, wc.data_ptr(),
+                      fb_c[k].data_ptr(), nl_c, rows, dys.data_ptr() + 32 * r0, None, wk_c.data_ptr(), nb_c, flags)
+        # sigma net -> dL/d(features)
+        _backend.call("ngp_ffmlp_backward_ex", dys.data_ptr() + 32 * r0, feat.data_ptr() + 4 * L * r0, ws.data_ptr(), fb_s[k].data_ptr(),
+                      rows, 2 * L, 16, 64, nl_s, 0, 6, 1, None, d_feat.data_ptr() + 4 * L * r0, None, wk_s.data_ptr(), nb_s, flags)
+        if piped:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        # hash-table scatter-add
+        with torch.cuda.stream(side if piped else main):
+            _backend.call("ngp_grid_encode_backward", d_feat.data_ptr() + 4 * L * r0, x01.data_ptr() + 12 * r0, None, offsets.data_ptr(),
+                          g_table.data_ptr(), rows, 3, 2, L, S, H, None, None, gridtype, align_corners, 0, 1, 0)
+    _backend.call("ngp_ffmlp_wgrad_finalize", wk_c.data_ptr(), gw_c.data_ptr(), nb_c // 4, 0)
+    _backend.call("ngp_ffmlp_wgrad_finalize", wk_s.data_ptr(), gw_s.data_ptr(), nb_s // 4, 0)
+    if piped:
+        main.wait_stream(side)
     return g_table, gw_s, gw_c
 
 
@@ -86,7 +140,7 @@ class _fused_field(Function):
     @staticmethod
     @custom_fwd(device_type='cuda')
     def forward(ctx, xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg):
-        sigma, rgb, stash = field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg)
+        sigma, rgb, stash = field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg, chunks=DEFAULT_CHUNKS)
         if stash is not None:
             ctx.save_for_backward(*stash["tensors"])
             ctx.cfg = stash["cfg"]

@@ -179,33 +179,136 @@ def train_step(model, rays_o, rays_d, target, optimizer=None, scaler=None, **ren
 
 class FusedTrainStep:
     """Autograd-free, host-sync-free training step: near/far -> march (steady-state budget) -> fused field
-    -> composite -> MSE -> composite backward -> fused field backward -> fused optimizer, all issued from one thread through
-    the C ABI, so the whole step can be captured in a CUDA graph and replayed.  Same arithmetic as train_step() with
-    NeRFFieldFF(fused=True) + FusedFieldOptimizer: the MSE gradient is formed in closed form instead of by autograd."""
+    -> composite -> MSE -> composite backward -> fused field backward -> exchange -> fused optimizer, all issued from one thread
+    through the C ABI, so the whole step can be captured in a CUDA graph and replayed.  Same arithmetic as train_step() with
+    NeRFFieldFF(fused=True) + FusedFieldOptimizer: the MSE gradient is formed in closed form instead of by autograd.
 
-    def __init__(self, model, optimizer, rays_total, bg_color=1.0, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, perturb=True):
+    Three things overlap inside a step (all joined before it returns, so a captured graph is self-contained):
+      * `chunks` > 1: the field is evaluated in row chunks; the color net of chunk k runs on a side stream under the encoder+sigma
+        kernel of chunk k+1, and in the backward the hash-table scatter of chunk k runs under the MLP backward kernels of chunk k+1
+        (nerf_fused.field_forward / field_backward);
+      * `prefetch(rays_o, rays_d)` marches the NEXT step's rays on a low-priority stream while this step's backward, gradient
+        exchange and optimizer run — the marcher is a latency-bound integer/ALU kernel that does not read the weights
+        (SURVEY §8e: "overlap must come from pipelining with the next step's R1/R5 march");
+      * at world size > 1 the fp16 gradient sink is all-reduced asynchronously (NCCL's stream) while the prefetched march finishes.
+    Samples live in two persistent (ping-pong) buffer sets sized for the model's steady-state budget `mean_count`."""
+
+    def __init__(self, model, optimizer, rays_total, bg_color=1.0, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, perturb=True,
+                 chunks=4, group=None, prefetch_point="start"):
         self.model, self.opt, self.R = model, optimizer, float(rays_total)
         self.bg, self.T_thresh, self.dt_gamma, self.max_steps, self.perturb = bg_color, T_thresh, dt_gamma, max_steps, perturb
+        self.chunks, self.group = int(chunks), group
+        assert prefetch_point in ("start", "exchange")
+        self.prefetch_point = prefetch_point     # where the next step's march is released: with the forward, or with the exchange
+        self._next = None                        # rays handed to step_prefetched(), marched inside body()
+        self._pending = False
+        self._slots = [None, None]      # marched sample sets (ping-pong)
+        self._cur = 0                   # slot the next body() consumes
+        self._ready = [False, False]
+        self._side = None               # field pipelining stream
+        self._march_stream = None       # prefetch stream (lowest priority)
+        dev = model.density_bitfield.device
+        self._ring = torch.zeros(1, dtype=torch.long, device=dev)        # next row of model.step_counter (device side)
+        self._nsteps = torch.zeros(1, dtype=torch.int32, device=dev)     # steps since the last sync_host_state()
+
+    # ---- sample generation -------------------------------------------------------------------------------------------------
+    def _streams(self):
+        if self._side is None:
+            # CUDA priorities: 0 is the LOWEST, negative is higher.  The prefetch march runs at the lowest priority; callers that want
+            # it to yield to the step's own kernels run the step on a higher-priority stream (bench.py does).
+            self._side = torch.cuda.Stream(priority=-1)
+            self._march_stream = torch.cuda.Stream(priority=0)
+        return self._side, self._march_stream
+
+    def _slot(self, i, n_rays):
+        m = self.model
+        assert m.mean_count > 0, "FusedTrainStep runs the steady-state (mean_count) path; establish the budget first"
+        M = m.mean_count + (128 - m.mean_count % 128)          # the reference's rule (raymarching.py:200-201)
+        s = self._slots[i]
+        if s is None or s["M"] != M or s["N"] != n_rays:
+            dev = m.density_bitfield.device
+            f = dict(dtype=torch.float32, device=dev)
+            s = dict(M=M, N=n_rays, xyzs=torch.zeros(M, 3, **f), dirs=torch.zeros(M, 3, **f), deltas=torch.zeros(M, 2, **f),
+                     rays=torch.zeros(n_rays, 3, dtype=torch.int32, device=dev), nears=torch.empty(n_rays, **f),
+                     fars=torch.empty(n_rays, **f), counter=torch.zeros(2, dtype=torch.int32, device=dev))
+            self._slots[i] = s
+        return s
 
     @torch.no_grad()
-    def __call__(self, rays_o, rays_d, target):
+    def _march_into(self, i, rays_o, rays_d):
+        """near/far + march of one ray batch into slot i, on the CURRENT stream."""
+        import _ngp_b200 as nb
+        m = self.model
+        o = rays_o.contiguous().view(-1, 3)
+        d = rays_d.contiguous().view(-1, 3)
+        n = o.shape[0]
+        s = self._slot(i, n)
+        nb.call("ngp_near_far_from_aabb", o.data_ptr(), d.data_ptr(), m.aabb_train.data_ptr(), n, float(m.min_near),
+                s["nears"].data_ptr(), s["fars"].data_ptr())
+        # rows the marcher does not reach must read as zeros (raymarching.py:205-207)
+        s["xyzs"].zero_(); s["dirs"].zero_(); s["deltas"].zero_(); s["counter"].zero_()
+        noise = torch.rand(n, dtype=torch.float32, device=o.device) if self.perturb else torch.zeros(n, dtype=torch.float32, device=o.device)
+        nb.call("ngp_march_rays_train", o.data_ptr(), d.data_ptr(), m.density_bitfield.data_ptr(), float(m.bound), float(self.dt_gamma),
+                int(self.max_steps), n, int(m.cascade), int(m.grid_size), s["M"], s["nears"].data_ptr(), s["fars"].data_ptr(),
+                s["xyzs"].data_ptr(), s["dirs"].data_ptr(), s["deltas"].data_ptr(), s["rays"].data_ptr(), s["counter"].data_ptr(),
+                noise.data_ptr())
+        # the reference's 16-slot sample-count ring (renderer.py:281-283), advanced on the device
+        m.step_counter.index_copy_(0, self._ring, s["counter"].view(1, 2))
+        self._ring.add_(1).remainder_(16)
+        self._nsteps.add_(1)
+        self._ready[i] = True
+
+    @torch.no_grad()
+    def march(self, rays_o, rays_d):
+        """Synchronous sample generation for the step that runs next."""
+        self._march_into(self._cur, rays_o, rays_d)
+
+    @torch.no_grad()
+    def prefetch(self, rays_o, rays_d):
+        """Start marching the FOLLOWING step's rays on the prefetch stream (ordered after the work queued so far on the current
+        stream); body() joins it before returning."""
+        _, ms = self._streams()
+        ms.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ms):
+            self._march_into(1 - self._cur, rays_o, rays_d)
+        self._pending = True
+
+    def set_slot(self, i):
+        """Re-synchronise the host-side slot bookkeeping after CUDA-graph replays (a replay runs no Python): step index i consumes
+        slot i % 2, which the previous step (or march()) filled."""
+        self._cur = int(i) % 2
+        self._ready[self._cur] = True
+
+    def sync_host_state(self):
+        """One host read: hand the number of steps taken since the last call to the model (`local_step`), as the reference's
+        update_extra_state expects before it re-estimates mean_count (renderer.py:532-536)."""
+        n = int(self._nsteps.item())
+        self._nsteps.zero_()
+        self.model.local_step = self.model.local_step + n
+        return n
+
+    # ---- the step ----------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def body(self, target):
+        """Forward, loss, backward, exchange and optimizer on the samples of the current slot; flips the slots afterwards."""
         import _ngp_b200 as nb
         from nerf_fused import field_forward, field_backward, field_cfg
         m = self.model
-        assert m.mean_count > 0, "FusedTrainStep runs the steady-state (mean_count) path; establish the budget first"
-        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, m.aabb_train, m.min_near)
-        counter = m.step_counter[0]
-        counter.zero_()
-        xyzs, dirs, deltas, rays = raymarching.march_rays_train(rays_o, rays_d, m.bound, m.density_bitfield, m.cascade,
-                                                                m.grid_size, nears, fars, counter, m.mean_count, self.perturb,
-                                                                128, False, self.dt_gamma, self.max_steps)
+        s = self._slots[self._cur]
+        assert s is not None and self._ready[self._cur], "no marched samples: call march() or prefetch() first"
+        side, ms = self._streams()
+        side_or_none = side if self.chunks > 1 else None
+        if self._next is not None and self.prefetch_point == "start":
+            self.prefetch(*self._next)
+            self._next = None
         cfg = field_cfg(m.encoder, m.sigma_net, m.color_net, m.bound, True)
-        sigma, rgb, stash = field_forward(xyzs, dirs, m.encoder.embeddings, m.encoder.offsets, m.sigma_net.weights,
-                                          m.color_net.weights, cfg)
+        sigma, rgb, stash = field_forward(s["xyzs"], s["dirs"], m.encoder.embeddings, m.encoder.offsets, m.sigma_net.weights,
+                                          m.color_net.weights, cfg, chunks=self.chunks, side=side_or_none)
         if m.density_scale != 1:
             sigma = sigma * m.density_scale
-        M, N = sigma.shape[0], rays.shape[0]
+        M, N = sigma.shape[0], s["N"]
         dev = sigma.device
+        deltas, rays = s["deltas"], s["rays"]
         wsum = torch.empty(N, device=dev); depth = torch.empty(N, device=dev); image = torch.empty(N, 3, device=dev)
         nb.call("ngp_composite_rays_train_forward", sigma.data_ptr(), rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), M, N,
                 float(self.T_thresh), wsum.data_ptr(), depth.data_ptr(), image.data_ptr())
@@ -213,14 +316,37 @@ class FusedTrainStep:
         diff = pred - target
         loss = (diff * diff).sum() / (3.0 * self.R)
         # d loss / d pred, scaled by the device-resident loss scale
-        g_pred = diff * ((2.0 / (3.0 * self.R)) * self.opt.scale_tensor())
-        g_ws = -(g_pred.sum(-1)) * self.bg
+        g_pred = (diff * ((2.0 / (3.0 * self.R)) * self.opt.scale_tensor())).contiguous()
+        g_ws = (-(g_pred.sum(-1)) * self.bg).contiguous()
         g_sigma = torch.zeros(M, device=dev); g_rgb = torch.zeros(M, 3, device=dev)
-        nb.call("ngp_composite_rays_train_backward", g_ws.contiguous().data_ptr(), g_pred.contiguous().data_ptr(), sigma.data_ptr(),
+        nb.call("ngp_composite_rays_train_backward", g_ws.data_ptr(), g_pred.data_ptr(), sigma.data_ptr(),
                 rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), wsum.data_ptr(), image.data_ptr(), M, N, float(self.T_thresh),
                 g_sigma.data_ptr(), g_rgb.data_ptr())
         if m.density_scale != 1:
             g_sigma = g_sigma * m.density_scale
-        field_backward(stash["tensors"], stash["cfg"], stash["sinks"], g_sigma, g_rgb)
-        self.opt.step()
+        field_backward(stash["tensors"], stash["cfg"], stash["sinks"], g_sigma, g_rgb, side=side_or_none)
+        if self._next is not None:                   # prefetch_point == "exchange": the march fills the communication bubble
+            self.prefetch(*self._next)
+            self._next = None
+        self.opt.begin_exchange(self.group)          # async all-reduce of the fp16 sink (world size > 1)
+        self.opt.finish_exchange()
+        self.opt.apply()
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(ms)
+            self._pending = False
+        self._ready[self._cur] = False
+        self._cur = 1 - self._cur
         return loss
+
+    @torch.no_grad()
+    def __call__(self, rays_o, rays_d, target):
+        """Unpipelined convenience form: march these rays now, then run the step on them."""
+        self.march(rays_o, rays_d)
+        return self.body(target)
+
+    @torch.no_grad()
+    def step_prefetched(self, target, next_rays_o, next_rays_d):
+        """Steady-state form: the current slot was filled by the previous call (or by march()); consume it with `target` while
+        the next step's rays are marched in the background."""
+        self._next = (next_rays_o, next_rays_d)
+        return self.body(target)

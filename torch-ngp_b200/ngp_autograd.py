@@ -9,7 +9,8 @@ One place for the four encoder / MLP ops the drop-in packages re-export under th
 
 Call signatures (positional order, defaults) and autocast contracts are the reference's: the grid op manages autocast itself
 (half table, float coordinates), the MLP casts its inputs to half, SH / frequency encodings are forced to float32.  Differences
-that are invisible to callers: kernels run on the current stream, the fp16 copy of the hash table is cached per parameter version,
+that are invisible to callers: kernels run on the current stream, the fp16 copy of the hash table is kept current by the fused
+optimizer when that owns the parameters (re-cast per forward otherwise, as in the reference),
 the MLP backward needs no [layers, B, hidden] scratch unless the net is deeper than the fused kernel supports.  No CPU path.
 """
 from collections import namedtuple
@@ -25,18 +26,46 @@ _call, _ptr = _backend.call, _backend.ptr
 
 
 def _half_table(embeddings):
-    """fp16 shadow of the table, cached ON the parameter object and invalidated by its autograd version counter
-    (optimizer steps bump it).  Keying by data_ptr would be wrong: freed tables get their address reused."""
-    ver = embeddings._version
+    """fp16 copy of the table for the kernels (reference gridencoder/grid.py:43-44 casts on every forward).
+
+    A cached copy is reused ONLY while ngp_optim.FusedFieldOptimizer owns it: that optimizer's Adam kernel rewrites the shadow in
+    place with every parameter update, so it is always current for updates made through it.  Any other writer (torch optimizers,
+    `.data` writes such as torch_ema copy_to()/restore(), reset_parameters, load_state_dict) is invisible to a cache — `.data`
+    writes do not even bump the autograd version counter — so without an owner the table is re-cast on every call, as the reference
+    does.  Owners that let someone else write the parameter call invalidate_half_table() (FusedFieldOptimizer.refresh_shadow)."""
     hit = getattr(embeddings, "_ngp_half_shadow", None)
-    if hit is not None and hit[0] == ver and hit[1].shape == embeddings.shape and hit[1].device == embeddings.device:
-        return hit[1]
+    if hit is not None and hit.shape == embeddings.shape and hit.device == embeddings.device:
+        return hit
+    return embeddings.detach().to(torch.half)
+
+
+def own_half_table(embeddings):
+    """Install (or refresh) the owner-maintained fp16 shadow of `embeddings`; returns it."""
+    hit = getattr(embeddings, "_ngp_half_shadow", None)
+    if hit is not None and hit.shape == embeddings.shape and hit.device == embeddings.device:
+        hit.copy_(embeddings.detach())
+        return hit
     half = embeddings.detach().to(torch.half)
-    try:
-        embeddings._ngp_half_shadow = (ver, half)
-    except Exception:
-        pass
+    embeddings._ngp_half_shadow = half
     return half
+
+
+def invalidate_half_table(embeddings):
+    if hasattr(embeddings, "_ngp_half_shadow"):
+        del embeddings._ngp_half_shadow
+
+
+def sync_half_table(embeddings):
+    """After an out-of-band write to `embeddings` (reset_parameters, load_state_dict): refresh an owner-maintained shadow in place
+    (its address stays valid for captured graphs); drop it if it no longer matches the parameter's shape / device."""
+    hit = getattr(embeddings, "_ngp_half_shadow", None)
+    if hit is None:
+        return
+    if hit.shape == embeddings.shape and hit.device == embeddings.device:
+        with torch.no_grad():
+            hit.copy_(embeddings.detach())
+    else:
+        invalidate_half_table(embeddings)
 
 
 # ------------------------------------------------------------------------------------------------ hash grid

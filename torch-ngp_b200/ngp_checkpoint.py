@@ -36,8 +36,9 @@ def load(path, model, optimizer=None, model_only=False, map_location=None):
     sd = ck["model"] if "model" in ck else ck
     missing, unexpected = model.load_state_dict(sd, strict=False)
     emb = getattr(getattr(model, "encoder", None), "embeddings", None)
-    if emb is not None and hasattr(emb, "_ngp_half_shadow"):
-        del emb._ngp_half_shadow                              # the fp16 kernel operand is rebuilt from the loaded master
+    if emb is not None:
+        from ngp_autograd import sync_half_table
+        sync_half_table(emb)                                  # an owner-maintained fp16 kernel operand follows the loaded master
     if "model" not in ck:
         return ck, list(missing), list(unexpected)
     if getattr(model, "cuda_ray", False):

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 import _ngp_b200 as _backend
-from gridencoder.grid import _half_table
+from ngp_autograd import own_half_table, invalidate_half_table
 
 
 class FusedFieldOptimizer:
@@ -26,8 +26,12 @@ class FusedFieldOptimizer:
         self.sink = torch.zeros(n, dtype=torch.half, device=dev)            # flat fp16 gradient bucket
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.state = torch.zeros(4, dtype=torch.int32, device=dev)          # {scale, growth_tracker, found_inf, step}
+        self.state = torch.zeros(8, dtype=torch.int32, device=dev)          # {scale, growth_tracker, found_inf, step, lr_scale, -, -, -}
         self.state[0:1].view(torch.float32).fill_(init_scale)
+        self.state[4:5].view(torch.float32).fill_(1.0)
+        # the fp16 kernel operand of the hash table is owned here: the Adam kernel rewrites it with every update
+        self.shadow = own_half_table(encoder.embeddings)
+        self._exchange = None
         self.segments = []
         off = 0
         for p in self.params:
@@ -41,18 +45,54 @@ class FusedFieldOptimizer:
         """Device scalar holding the current loss scale: `(loss * opt.scale_tensor()).backward()`."""
         return self.state[0:1].view(torch.float32)
 
+    def set_lr_scale(self, factor):
+        """LambdaLR-style schedule: the step size becomes lr * factor.  A device scalar, so it also takes effect in a captured graph."""
+        self.state[4:5].view(torch.float32).fill_(float(factor))
+
+    def refresh_shadow(self):
+        """Call after anything else wrote the hash table (`.data` writes such as EMA copy_to()/restore(), load_state_dict)."""
+        self.shadow = own_half_table(self.encoder.embeddings)
+
     def detach(self):
         for p in self.params:
             if hasattr(p, "_ngp_grad_sink"):
                 del p._ngp_grad_sink
+        invalidate_half_table(self.encoder.embeddings)
+
+    @torch.no_grad()
+    def _absorb_autograd_grads(self):
+        """Gradients that arrived through autograd (module-by-module path, grad_total_variation) instead of the fp16 sink are folded
+        into the sink, so nothing is silently dropped.  They carry the same loss scale (the caller scaled the loss)."""
+        for p, off, k in self.segments:
+            if p.grad is not None:
+                self.sink[off:off + k].add_(p.grad.reshape(-1).to(torch.half))
+                p.grad = None
+
+    def begin_exchange(self, group=None):
+        """Launch the step's only exchange (sum-allreduce of the fp16 sink) without blocking the current stream: NCCL runs it on
+        its own stream after the work queued so far; finish_exchange() makes the current stream wait for it."""
+        self._absorb_autograd_grads()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self._exchange = dist.all_reduce(self.sink, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def finish_exchange(self):
+        if self._exchange is not None:
+            self._exchange.wait()
+            self._exchange = None
 
     @torch.no_grad()
     def step(self, group=None):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.sink, op=dist.ReduceOp.SUM, group=group)   # the step's only exchange
+        if self._exchange is None:
+            self.begin_exchange(group)
+        self.finish_exchange()
+        self.apply()
+
+    @torch.no_grad()
+    def apply(self):
+        """inf check + Adam + fp16 shadow refresh + gradient zeroing + GradScaler update on the (already reduced) sink."""
         _backend.call("ngp_optim_check_finite", self.sink.data_ptr(), 1, self.sink.numel(), self.state.data_ptr())
         for p, off, k in self.segments:
-            shadow = _half_table(p) if p is self.encoder.embeddings else None    # refreshed in place by the kernel
+            shadow = self.shadow if p is self.encoder.embeddings else None    # refreshed in place by the kernel
             _backend.call("ngp_optim_adam_step", p.data_ptr(), self.exp_avg.data_ptr() + 4 * off,
                           self.exp_avg_sq.data_ptr() + 4 * off, self.sink.data_ptr() + 2 * off, 1, _backend.ptr(shadow), k,
                           float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
