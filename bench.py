@@ -243,8 +243,10 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "nerf_train_800x800_synthetic_lego_boxes", "rays_per_step": args.cpu_rays,
-                           "note": "reference pure-PyTorch path (--fp32, no --cuda_ray) restated for CPU; bounded sample of the GPU arm's workload"},
+                "config": {"workload": "nerf_train_800x800_synthetic_lego_boxes", "rays_per_step": args.rays_per_step,
+                           "hashgrid": "L=16 F=2 T=2^19 base16 ->2048",
+                           "note": f"reference pure-PyTorch path (--fp32, no --cuda_ray; renderer.py:125-253 `run`, 512 samples/ray) on the host cores; each step is a "
+                                   f"bounded sample of {args.cpu_rays} rays of the same 800x800 frame (cpu_baseline.sample)"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -253,6 +255,13 @@ def main():
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: CUDA device required (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    if args.config != "c2":
+        # the other BASELINE.json configs: single-GPU op / inference throughput arms (bench_configs.py); one JSON line each
+        if rank == 0:
+            import bench_configs
+            bench_configs.main(args)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -609,19 +618,19 @@ def main():
         line["cpu_baseline"] = r.get("cpu_baseline", {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                                       "sample": "failed: " + str(r.get("unavailable"))})
     if rank == 0 and world == 1 and not args.no_ref_cuda and not args.unfused:
-        # the unchanged-caller path: module-by-module field (GridEncoder -> FFMLP -> ... as nerf/network_ff.py calls them),
-        # autograd, GradScaler + torch Adam — what a torch-ngp user gets by only swapping the four packages
-        log("drop-in (unfused) path (child process)")
+        # the unchanged-caller path: the reference's own nerf/network_ff.py + nerf/renderer.py (unmodified, staged under oracle/_ref/py)
+        # over this repo's four drop-in packages, autograd, GradScaler + torch Adam — what a torch-ngp user gets by swapping the
+        # package directories and nothing else.  Deferred tensors (ngp_lazy) route the module sequence to the fused kernels.
+        log("drop-in path: reference callers over our packages (child process)")
         torch.cuda.empty_cache()
-        r = child([sys.executable, os.path.join(ROOT, "bench.py"), "--unfused", "--torch-optimizer", "--no-cpu-baseline", "--no-ref-cuda",
-                   "--rays-per-step", str(R), "--steps", "5", "--warmup", "3"], 200)
-        line["dropin_unfused"] = ({"value": r.get("value"), "unit": UNIT, "ms_per_step": r.get("ms_per_step"),
-                                   "what": "same step through the reference-shaped modules only (no fused field, no fused optimizer, no graph)"}
-                                  if "value" in r else r)
+        line["dropin"] = child([sys.executable, os.path.join(ROOT, "bench_ref_cuda.py"), "--stack", "ours", "--rays-per-step", str(R),
+                                "--steps", "8"], 300)
+        line["dropin_literal"] = child([sys.executable, os.path.join(ROOT, "bench_ref_cuda.py"), "--stack", "ours", "--no-lazy",
+                                        "--rays-per-step", str(R), "--steps", "5"], 300)
     if rank == 0 and world == 1 and not args.no_ref_cuda:
         log("reference CUDA build arm (child process)")
         torch.cuda.empty_cache()
-        line["ref_cuda"] = child([sys.executable, os.path.join(ROOT, "bench_ref_cuda.py"), "--rays-per-step", str(R),
+        line["ref_cuda"] = child([sys.executable, os.path.join(ROOT, "bench_ref_cuda.py"), "--stack", "ref", "--rays-per-step", str(R),
                                   "--steps", str(max(3, min(args.steps, 10)))], 300)
     if rank == 0:
         emit(line)

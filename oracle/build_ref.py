@@ -14,6 +14,12 @@ shencoder/src/bindings.cpp:6-7, raymarching/src/bindings.cpp:7-18) and are used
   * by tests/golden/make_golden.py to generate committed golden vectors,
   * by bench.py as the "reference CUDA build" timing arm (reported beside ours).
 
+ship_python() additionally stages the reference's own PYTHON on the path — the callers (encoding.py, activation.py, nerf/, sdf/)
+under oracle/_ref/py/callers and the four wrapper packages under oracle/_ref/py/wrappers — byte for byte, so that the GPU box (which
+has no /root/reference) can run the unmodified nerf/network_ff.py + nerf/renderer.py over either this repo's drop-in packages or the
+reference's wrappers + extensions (oracle/ref_stack.py).  Like the .so files these copies are git-ignored build outputs of this
+recipe, travel with the gpurun snapshot, and are never imported by anything under torch-ngp_b200/.
+
 Usage:  python oracle/build_ref.py [gridencoder shencoder raymarching ffmlp]
 """
 import os
@@ -65,5 +71,30 @@ def build(names=None, verbose=False):
     return [so_path(n) for n in names]
 
 
+PY_CALLERS = ["encoding.py", "activation.py", "loss.py", "nerf/network_ff.py", "nerf/network.py", "nerf/renderer.py", "nerf/utils.py",
+              "sdf/netowrk_ff.py", "sdf/netowrk.py"]
+PY_WRAPPERS = ["gridencoder/__init__.py", "gridencoder/grid.py", "ffmlp/__init__.py", "ffmlp/ffmlp.py",
+               "shencoder/__init__.py", "shencoder/sphere_harmonics.py", "raymarching/__init__.py", "raymarching/raymarching.py"]
+
+
+def ship_python():
+    """Copy the reference's Python files of the path (unmodified) into oracle/_ref/py/{callers,wrappers}; returns the file list."""
+    import shutil
+    if not os.path.isdir(REF):
+        raise RuntimeError(f"reference tree {REF} not present (it only exists in the build container)")
+    done = []
+    for sub, files in (("callers", PY_CALLERS), ("wrappers", PY_WRAPPERS)):
+        for rel in files:
+            src = os.path.join(REF, rel)
+            if not os.path.exists(src):
+                continue
+            dst = os.path.join(OUT, "py", sub, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(src, dst)
+            done.append(dst)
+    return done
+
+
 if __name__ == "__main__":
     print(build(sys.argv[1:] or None, verbose=True))
+    print(ship_python())

@@ -26,12 +26,21 @@ def test_config3_fused_density_inference_4096x1024():
     pts = (rays_o[:, None, :] + rays_d[:, None, :] * t[None, :, None]).clamp(-1, 1).reshape(-1, 3).cuda()
     M = pts.shape[0]
     assert M == 4096 * 1024
+    import ngp_lazy
+    ngp_lazy.enabled = False
+    try:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            ref = m.density(pts)["sigma"]                              # literal module sequence, inference kernels
+    finally:
+        ngp_lazy.enabled = True
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-        ref = m.density(pts)["sigma"]                                  # unfused modules, inference kernels
+        via_modules = m.density(pts)["sigma"]                          # the same call, deferred-tensor fusion on (default)
+    assert torch.equal(via_modules, ref)
     x01 = ((pts + 1) / 2).contiguous()
+    table = _half_table(m.encoder.embeddings)
     h = torch.empty(M, 16, dtype=torch.half, device="cuda"); sig = torch.empty(M, device="cuda")
     w = m.sigma_net.weights.detach().half()
-    nb.call("ngp_field_sigma_forward", x01.data_ptr(), _half_table(m.encoder.embeddings).data_ptr(), m.encoder.offsets.data_ptr(),
+    nb.call("ngp_field_sigma_forward", x01.data_ptr(), table.data_ptr(), m.encoder.offsets.data_ptr(),
             16, float(np.log2(m.encoder.per_level_scale)), 16, 0, 0, w.data_ptr(), 2, M, 0, None, None, h.data_ptr(), sig.data_ptr())
     assert rel_err(sig.cpu().numpy(), ref.float().cpu().numpy()) < 1e-6
     # oracle on the first 2048 points

@@ -144,3 +144,69 @@ def test_resume_from_reference_adam_state():
     assert float(sd["state"][0]["step"]) == 4.0
     assert rel_err(sd["state"][2]["exp_avg_sq"].cpu().numpy(), ref.state_dict()["state"][2]["exp_avg_sq"].cpu().numpy()) < 1e-5
     fused.detach()
+
+
+def _fresh_field(grid):
+    from nerf_step import NeRFFieldFF
+    from ngp_optim import FusedFieldOptimizer
+    import ngp_synth as S
+    torch.manual_seed(1)
+    model = NeRFFieldFF(bound=1, fused=True).cuda().train()
+    with torch.no_grad():
+        model.encoder.embeddings.uniform_(-0.3, 0.3)
+    model.density_bitfield.copy_(torch.from_numpy(S.packbits_np(grid.numpy())).cuda())
+    opt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, init_scale=1024.0)
+    model.mean_count = 200000
+    return model, opt
+
+
+def test_pipelined_prefetched_steps_match_sequential_and_capture():
+    """step_prefetched (march of step i+1 on the prefetch stream, 4 field chunks on the side stream) == the plain sequential step;
+    the same call captured in two CUDA graphs (even / odd sample slot) and replayed continues the sequence."""
+    from nerf_step import FusedTrainStep
+    import ngp_synth as S
+    from util import synth_rays
+    N, K = 8192, 4
+    grid, _ = S.box_union_density(128, seed=12)
+    rays = [tuple(t.cuda() for t in synth_rays(N, seed=s)[:2]) for s in range(K + 1)]
+    tgts = [torch.rand(N, 3, generator=gen(40 + s)).cuda() for s in range(K + 1)]
+    # A: sequential, unchunked
+    ma, oa = _fresh_field(grid)
+    fa = FusedTrainStep(ma, oa, N, perturb=False, chunks=1)
+    la = [float(fa(rays[i][0], rays[i][1], tgts[i])) for i in range(K)]
+    # B: prefetched + chunked, eager
+    mb, ob = _fresh_field(grid)
+    fb = FusedTrainStep(mb, ob, N, perturb=False, chunks=4)
+    fb.march(*rays[0])
+    lb = [float(fb.step_prefetched(tgts[i], *rays[i + 1])) for i in range(K)]
+    assert int(ob.state[3].item()) == K and int(oa.state[3].item()) == K
+    # same samples (bit-exact marcher), same arithmetic up to fp16 atomics order; Adam's early sign-like steps amplify that a little
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (la, lb)
+    assert la[-1] < la[0]
+    assert fb.sync_host_state() == K + 1 and mb.local_step == K + 1          # K + 1 marches were recorded in the ring
+    # C: the same call under CUDA-graph capture (what bench.py replays)
+    mc, oc = _fresh_field(grid)
+    fc = FusedTrainStep(mc, oc, N, perturb=False, chunks=4)
+    st_o, st_d, st_t = torch.empty_like(rays[0][0]), torch.empty_like(rays[0][1]), torch.empty_like(tgts[0])
+    hp = torch.cuda.Stream(priority=-1)
+    hp.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(hp):
+        fc.march(*rays[0])
+        lc = [float(fc.step_prefetched(tgts[i], *rays[i + 1])) for i in range(2)]        # eager warm-up: steps 0, 1
+    torch.cuda.current_stream().wait_stream(hp)
+    torch.cuda.synchronize()
+    graphs, losses = [], []
+    for par in range(2):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=hp):
+            losses.append(fc.step_prefetched(st_t, st_o, st_d))
+        graphs.append(g)
+    torch.cuda.synchronize()
+    for i in range(2, K):
+        st_t.copy_(tgts[i]); st_o.copy_(rays[i + 1][0]); st_d.copy_(rays[i + 1][1])
+        graphs[i % 2].replay()
+        lc.append(float(losses[i % 2]))
+    assert int(oc.state[3].item()) == K
+    for x, y in zip(la, lc):
+        assert abs(x - y) <= 2e-3 * max(abs(x), 1e-6), (la, lc)

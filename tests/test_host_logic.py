@@ -89,3 +89,21 @@ def test_reference_callers_import_unchanged():
         sys.path.remove("/root/reference")
         for k in [k for k in sys.modules if k.startswith(("nerf", "sdf", "encoding", "activation"))]:
             sys.modules.pop(k, None)
+
+
+def test_staged_reference_python_runs_over_the_dropin_packages():
+    """oracle/ref_stack: the staged, unmodified reference callers construct over this repo's packages (CPU: construction only; the
+    device-side parity of the two stacks is tests/test_gpu_reference_callers.py)."""
+    from oracle import ref_stack
+    if not ref_stack.available("ours"):
+        pytest.skip("oracle/_ref/py not staged (python oracle/build_ref.py where /root/reference exists)")
+    st = ref_stack.load("ours")
+    model = ref_stack.make_nerf(st, bound=1)
+    assert type(model).__module__ == "nerf.network_ff" and type(model).__mro__[1].__module__ == "nerf.renderer"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert os.path.dirname(type(model.encoder).__module__ and sys.modules[type(model.sigma_net).__module__].__file__).startswith(os.path.join(root, "torch-ngp_b200"))
+    assert "nerf.network_ff" not in sys.modules          # the stack's modules do not leak into the session
+    sdf = st.module("sdf.netowrk_ff")
+    with st.active():
+        net = sdf.SDFNetwork()
+    assert net.backbone.weights.shape == (64 * (32 + 64 * 2 + 16),)

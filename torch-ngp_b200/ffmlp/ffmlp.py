@@ -33,6 +33,12 @@ class FFMLP(nn.Module):
         assert input_dim > 0 and input_dim % 16 == 0, f"FFMLP: input_dim {input_dim} must be a positive multiple of 16"
         assert output_dim <= 16, f"FFMLP: output_dim {output_dim} > 16 is not supported"
         assert num_layers >= 2, f"FFMLP: num_layers {num_layers} < 2 (at least 3 matmuls)"
+        # capability of THIS build, stated at construction instead of at the first forward (csrc/ffmlp.cu check_cfg): the tcgen05 kernels
+        # are instantiated for 64 hidden units, at most 64 inputs and at most 8 hidden layers — what torch-ngp's NeRF / SDF networks use
+        if hidden_dim != 64 or input_dim > 64 or num_layers > 8:
+            raise NotImplementedError(f"FFMLP (B200 build): hidden_dim must be 64, input_dim <= 64, num_layers <= 8 "
+                                      f"(got hidden_dim={hidden_dim}, input_dim={input_dim}, num_layers={num_layers}); the reference "
+                                      f"additionally offers hidden widths 16/32/128/256 (ffmlp/src/ffmlp.cu:653-657)")
         self.input_dim, self.output_dim, self.hidden_dim, self.num_layers = input_dim, output_dim, hidden_dim, num_layers
         self.activation = convert_activation(activation)
         self.output_activation = ACT_NONE                          # the reference supports none either (ffmlp.py:108)
@@ -57,7 +63,18 @@ class FFMLP(nn.Module):
                 f"num_layers={self.num_layers} activation={self.activation}")
 
     def forward(self, inputs):
-        """inputs [B, input_dim] -> [B, output_dim] (half under autocast)"""
+        """inputs [B, input_dim] -> [B, output_dim] (half under autocast).  A deferred GridEncoder / SH-concat input (ngp_lazy) is
+        consumed by the fused encoder->MLP kernel; the result is the same tensor the two separate ops would give."""
+        import ngp_lazy
+        if isinstance(inputs, ngp_lazy.Deferred):
+            fused = None
+            if isinstance(inputs, ngp_lazy.DeferredGridFeatures):
+                fused = ngp_lazy.grid_mlp(inputs, self)
+            elif isinstance(inputs, ngp_lazy.DeferredColorInput):
+                fused = ngp_lazy.color_mlp(inputs, self)
+            if fused is not None:
+                return fused
+            inputs = inputs.materialize()
         y = ffmlp_forward(inputs, self.weights, self.input_dim, self.padded_output_dim, self.hidden_dim, self.num_layers,
                           self.activation, self.output_activation, not self.training, inputs.requires_grad)
         return y if self.padded_output_dim == self.output_dim else y[:, :self.output_dim]

@@ -66,7 +66,14 @@ class GridEncoder(nn.Module):
                 f"interpolation={self.interpolation}")
 
     def forward(self, inputs, bound=1):
-        """inputs [..., input_dim] in [-bound, bound] -> [..., num_levels * level_dim]"""
+        """inputs [..., input_dim] in [-bound, bound] -> [..., num_levels * level_dim].
+        Where the fused encoder->MLP kernel reproduces this op exactly (ngp_lazy.defer_grid) the result is a deferred tensor: a
+        drop-in FFMLP consumes it without the features ever reaching HBM, anything else materialises it through _forward_eager."""
+        import ngp_lazy
+        deferred = ngp_lazy.defer_grid(self, inputs, bound)
+        return deferred if deferred is not None else self._forward_eager(inputs, bound)
+
+    def _forward_eager(self, inputs, bound=1):
         unit = (inputs + bound) / (2 * bound)          # kept as a torch op so autograd w.r.t. the coordinates works
         lead = list(unit.shape[:-1])
         flat = unit.view(-1, self.input_dim)

@@ -16,7 +16,14 @@ class SHEncoder(nn.Module):
         return f"SHEncoder: input_dim={self.input_dim} degree={self.degree}"
 
     def forward(self, inputs, size=1):
-        """inputs [..., 3] in [-size, size] -> [..., degree^2] (float32)"""
+        """inputs [..., 3] in [-size, size] -> [..., degree^2] (float32).  Degree-4 encodings of [M,3] directions are returned as a
+        deferred tensor (ngp_lazy): `torch.cat([sh, geo_feat, pad])` followed by a drop-in FFMLP then runs as one fused kernel; any
+        other use materialises it through _forward_eager."""
+        import ngp_lazy
+        deferred = ngp_lazy.defer_sh(self, inputs, size)
+        return deferred if deferred is not None else self._forward_eager(inputs, size)
+
+    def _forward_eager(self, inputs, size=1):
         scaled = inputs / size
         flat = scaled.reshape(-1, self.input_dim)
         basis = sh_encode(flat, self.degree, flat.requires_grad)
