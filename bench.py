@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the steady-state step in a CUDA graph")
     ap.add_argument("--torch-optimizer", action="store_true", help="GradScaler + torch fused Adam on fp32 .grad (reference trainer sequence) instead of the fused fp16-sink optimizer kernel")
     ap.add_argument("--unfused", action="store_true", help="evaluate the field module by module (network_ff.py call sequence) instead of the fused field kernels")
-    ap.add_argument("--chunks", type=int, default=4, help="row chunks of the fused field (side-stream pipelining of color fwd / table scatter); 1 = off")
+    ap.add_argument("--chunks", type=int, default=1, help="row chunks of the fused field (side-stream pipelining of color fwd / table scatter); 1 = off")
     ap.add_argument("--no-prefetch", action="store_true", help="march each step's rays inside that step instead of one step ahead on a low-priority stream")
     ap.add_argument("--prefetch-point", default="auto", choices=["auto", "start", "exchange"])
     ap.add_argument("--long-steps", type=int, default=200, help="extra, longer timed region reported as `long_run` (0 = skip)")

@@ -183,6 +183,33 @@ int ngp_field_color_backward(const float* d_rgb, const float* rgb, const float* 
                              uint32_t num_layers, uint32_t M, void* dys_out, void* grad_weights, void* workspace,
                              size_t workspace_bytes, ngp_stream_t stream);
 
+/* ---- device-driven inference loop (extension).  The reference's eval loop (nerf/renderer.py:337-367) sizes every iteration on the
+ * host from `rays_alive[rays_alive >= 0]` (a boolean-index copy + synchronisation per iteration).  Here the loop state is a device
+ * control block ctrl[8] u32 = {n_alive, n_step = max(min(N / n_alive, 8), 1), M = n_alive * n_step padded to 128, samples marched so
+ * far, scratch, ...}; every kernel is launched for the worst case (N rays / M_max rows) and reads its real extent from ctrl, so an
+ * iteration needs no host round trip and a block of iterations can be captured in a CUDA graph.  Per-ray arithmetic, n_step schedule
+ * and termination rule are those of ngp_march_rays / ngp_composite_rays; only the order of the compacted ray list differs. ---- */
+int ngp_infer_init(uint32_t N, int32_t* rays_alive, uint32_t* ctrl, ngp_stream_t stream);
+/* as ngp_march_rays with (n_alive, n_step) = ctrl[0..1]; writes a delta == 0 sentinel after a ray's last sample instead of requiring
+ * zero-filled buffers; noises (nullable) are applied in the first iteration only (renderer.py:353). */
+int ngp_march_rays_dev(const uint32_t* ctrl, uint32_t N, const int32_t* rays_alive, const float* rays_t,
+                       const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                       uint32_t C, uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs,
+                       float* deltas, const float* noises, ngp_stream_t stream);
+int ngp_composite_rays_dev(const uint32_t* ctrl, uint32_t N, float T_thresh, int32_t* rays_alive, float* rays_t,
+                           const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                           float* depth, float* image, ngp_stream_t stream);
+/* survivors (rays_in[n] >= 0) -> rays_out, then ctrl for the next iteration (n_alive = 0 once max_steps samples were marched) */
+int ngp_compact_rays_dev(uint32_t* ctrl, uint32_t N, uint32_t max_steps, const int32_t* rays_in, int32_t* rays_out,
+                         ngp_stream_t stream);
+/* fused field kernels reading their row count on the device (rows = min(M_max, *rows_dev)); xyz in WORLD coordinates */
+int ngp_field_sigma_forward_dev(const float* xyz, float bound, const uint32_t* rows_dev, const void* table_f16,
+                                const int32_t* offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                int align_corners, const void* weights, uint32_t num_layers, uint32_t M_max, void* h_out,
+                                float* sigma_out, ngp_stream_t stream);
+int ngp_field_color_forward_dev(const float* dirs, const void* h_sigma, const uint32_t* rows_dev, const void* weights,
+                                uint32_t num_layers, uint32_t M_max, float* rgb_out, ngp_stream_t stream);
+
 /* General form: the output gradient either as (d_rgb, rgb) [sigmoid gradient formed in the kernel] or as grad_h [M,3] fp16 =
  * dL/d(network output); d_sigma nullable (column 0 of dys_out is then 0: the caller's autograd handles trunc_exp); pad as in the
  * forward; flags = NGP_WGRAD_* as ngp_ffmlp_backward_ex. */

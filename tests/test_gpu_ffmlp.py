@@ -69,7 +69,7 @@ def test_forward_inference_vs_oracle(cfg, B):
     assert (fb >= 0).all()
 
 
-@pytest.mark.parametrize("act", [0, 1, 3, 4, 5, 6])
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4, 5, 6])      # ReLU, exp, sine, sigmoid, squareplus, softplus, none (ffmlp.py:89-96)
 def test_activations(act):
     from oracle import oracle as O
     import _ngp_b200 as nb
@@ -198,6 +198,85 @@ def test_vs_reference_extension():
         assert rel_err(bb.cpu().numpy(), bbr.cpu().numpy()) < 5e-3
         assert rel_err(gi.cpu().numpy(), gir.cpu().numpy()) < 5e-3
         assert rel_err(gw.float().cpu().numpy(), gwr.float().cpu().numpy()) < 2e-2
+
+
+def _truth64(x16, w16, ind, nl):
+    """The exact real-arithmetic MLP of the fp16 inputs / weights: float64 products and sums, NO intermediate rounding."""
+    from oracle import oracle as O
+    mats = O.mlp_split_weights(np.asarray(w16, dtype=np.float16), ind, 64, nl)
+    h = np.asarray(x16, dtype=np.float64)
+    hid = []
+    for W in mats[:-1]:
+        h = np.maximum(h @ W.astype(np.float64).T, 0)
+        hid.append(h)
+    return h @ mats[-1].astype(np.float64).T, hid
+
+
+def test_fp32_accumulation_is_closer_to_the_fp64_truth_than_the_reference():
+    """The op-level tolerances against the reference extension (3e-3 forward, 2e-2 weight gradients) are the REFERENCE's error, not
+    ours: it accumulates in fp16 inside wmma and in its fp16 split-K reduce (ffmlp.cu:68,564; cutlass_matmul.h:81-82,467-468), this
+    library in fp32 in TMEM.  Checked against the float64 value of the same fp16 inputs / weights: element-wise our outputs are
+    within the bound that the shared fp16 rounding of the stored activations allows, and by every aggregate our error is no larger
+    than the reference's."""
+    from oracle import ref_driver as R
+    import _ngp_b200 as nb
+    B = 128 * 64
+    report = []
+    for cfg in (dict(input_dim=32, num_layers=2), dict(input_dim=32, num_layers=3)):
+        x, w = _mk(B, **cfg)
+        nl, ind = cfg["num_layers"], cfg["input_dim"]
+        xd, wd = x.cuda(), w.cuda()
+        y64, hid64 = _truth64(x.numpy(), w.numpy(), ind, nl)
+        fb = torch.empty(nl, B, 64, dtype=torch.half, device="cuda"); y = torch.empty(B, 16, dtype=torch.half, device="cuda")
+        nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), B, ind, 16, 64, nl, 0, 6, fb.data_ptr(), y.data_ptr())
+        ours = y.float().cpu().numpy().astype(np.float64)
+        e_ours = np.abs(ours - y64)
+        rms = np.sqrt((y64 ** 2).mean())
+        # element-wise, layer by layer: every STORED fp16 activation / output equals the float64 contraction of the layer's own stored
+        # fp16 inputs rounded once — half an fp16 ulp (2^-11 relative) plus the fp32 accumulation slack.  This is the north_star's
+        # "within 1e-3 rel" statement per element (2^-11 = 4.9e-4).
+        from oracle import oracle as O
+        mats = O.mlp_split_weights(w.numpy(), ind, 64, nl)
+        worst = 0.0
+        prev = x.numpy().astype(np.float64)
+        for l in range(nl + 1):
+            pre = prev @ mats[l].astype(np.float64).T
+            want = np.maximum(pre, 0) if l < nl else pre
+            got = (fb[l] if l < nl else y).float().cpu().numpy().astype(np.float64)
+            tol = 2.0 ** -11 * np.abs(want) * 1.0005 + 2e-6 * np.sqrt((want ** 2).mean()) + 6e-8       # + fp16 subnormal spacing
+            worst = max(worst, float((np.abs(got - want) / tol).max()))
+            assert (np.abs(got - want) <= tol).all(), (l, float((np.abs(got - want) / tol).max()))
+            prev = got
+        line = (f"nl={nl}: per-layer element-wise error / (half fp16 ulp) max {worst:.3f}; end-to-end vs unrounded float64: ours max {e_ours.max():.3e} "
+                f"rms {np.sqrt((e_ours ** 2).mean()):.3e} (output rms {rms:.3f})")
+        if R.available("ffmlp"):
+            yr, fbr = R.ffmlp_forward(xd, wd, ind, 16, 64, nl)
+            e_ref = np.abs(yr.float().cpu().numpy().astype(np.float64) - y64)
+            assert np.sqrt((e_ours ** 2).mean()) <= np.sqrt((e_ref ** 2).mean())
+            assert e_ours.max() <= e_ref.max()
+            assert (e_ours > e_ref + 2.0 ** -11 * np.abs(y64) + 1e-12).mean() < 0.35          # worse than the reference by > 1/2 ulp: a minority
+            line += f" | reference ext max {e_ref.max():.3e} rms {np.sqrt((e_ref ** 2).mean()):.3e}"
+            # weight gradients against the float64 contraction of the SAME fp16 dPre / activations (both sides round those alike)
+            g = (torch.randn(B, 16, generator=gen(5)) * 0.01).half().cuda()
+            gir, gwr, bbr = R.ffmlp_backward(g, xd, wd, fbr, ind, 16, 64, nl)
+            gw = torch.zeros_like(wd); gi = torch.zeros_like(xd); bb = torch.zeros_like(bbr)
+            nbytes = nb.load().ngp_ffmlp_backward_workspace_bytes(B, ind, 16, 64, nl)
+            ws = torch.empty(nbytes // 4, device="cuda")
+            nb.call("ngp_ffmlp_backward", g.data_ptr(), xd.data_ptr(), wd.data_ptr(), fbr.data_ptr(), B, ind, 16, 64, nl, 0, 6, 1,
+                    bb.data_ptr(), gi.data_ptr(), gw.data_ptr(), ws.data_ptr(), nbytes)
+            # truth for the output-layer weight gradient: dY^T @ H_last in float64 (no dependence on either side's dPre rounding)
+            H = fbr[nl - 1].float().cpu().numpy().astype(np.float64)
+            gw_out64 = g.float().cpu().numpy().astype(np.float64).T @ H                      # [16, 64]
+            n_out = 16 * 64
+            ours_out = gw.float().cpu().numpy()[-n_out:].reshape(16, 64).astype(np.float64)
+            ref_out = gwr.float().cpu().numpy()[-n_out:].reshape(16, 64).astype(np.float64)
+            eo, er = np.abs(ours_out - gw_out64), np.abs(ref_out - gw_out64)
+            assert np.sqrt((eo ** 2).mean()) <= np.sqrt((er ** 2).mean()) and eo.max() <= er.max()
+            scale = np.abs(gw_out64).max()
+            assert eo.max() <= 2.0 ** -10 * scale + 1e-12                                   # ours: one fp16 rounding of an fp32 sum
+            line += f" | out-layer dW: ours max {eo.max() / scale:.2e}, reference {er.max() / scale:.2e} (of max |dW|)"
+        report.append(line)
+    print("\n".join(report))
 
 
 def test_errors():

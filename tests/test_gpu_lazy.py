@@ -34,10 +34,10 @@ def _run(m, x, d, lazy):
         nb.profile_begin()
         with torch.autocast("cuda", dtype=torch.float16):
             sigma, rgb = m(x, d)
-            loss = (sigma.float() * 0.01).sum() + (rgb.float() * torch.linspace(0.5, 1.5, 3, device=x.device)).sum()
-        (loss * 64.0).backward()
+            loss = ((sigma.float() * 0.01).sum() + (rgb.float() * torch.linspace(0.5, 1.5, 3, device=x.device)).sum()) / x.shape[0]
+        loss.backward()
         calls = [r[0] for r in nb.profile_end()]
-        g = [p.grad.detach().float().clone() / 64.0 for p in (m.encoder.embeddings, m.sigma_net.weights, m.color_net.weights)]
+        g = [p.grad.detach().float().clone() for p in (m.encoder.embeddings, m.sigma_net.weights, m.color_net.weights)]
         return sigma.detach().float(), rgb.detach().float(), g, calls
     finally:
         ngp_lazy.enabled = True
@@ -56,6 +56,7 @@ def test_network_ff_sequence_fuses_and_matches_eager():
     assert torch.equal(s0, s1)
     assert float((c0 - c1).abs().max()) <= 2e-3 and float(((c0 - c1).abs() > 0).float().mean()) < 0.05
     for a, b, tol in zip(g0, g1, (3e-2, 1e-2, 1e-2)):          # table: fp16 atomics order
+        assert torch.isfinite(a).all() and torch.isfinite(b).all() and float(a.abs().max()) > 0
         assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < tol
 
 

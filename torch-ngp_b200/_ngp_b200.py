@@ -35,6 +35,12 @@ _SIGNATURES = {
     "ngp_field_color_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _vp],
     "ngp_field_color_forward_ex": [_vp, _vp, _vp, _vp, _u32, _u32, _i32, _vp, _vp, _vp, _vp],
     "ngp_field_color_backward_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _sz, _u32, _vp],
+    "ngp_infer_init": [_u32, _vp, _vp, _vp],
+    "ngp_march_rays_dev": [_vp, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_composite_rays_dev": [_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_compact_rays_dev": [_vp, _u32, _u32, _vp, _vp, _vp],
+    "ngp_field_sigma_forward_dev": [_vp, _f32, _vp, _vp, _vp, _u32, _f32, _u32, _u32, _i32, _vp, _u32, _u32, _vp, _vp, _vp],
+    "ngp_field_color_forward_dev": [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp],
     "ngp_debug_umma": [_vp, _vp, _vp, _i32, _vp],
     "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
     "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],

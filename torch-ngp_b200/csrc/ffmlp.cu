@@ -70,6 +70,8 @@ struct FieldArgs {
     const float* d_sigma;    // [M] (nullable: column 0 of dys_out is then 0 — trunc_exp handled by the caller)
     const __half* grad_h;    // [M,3] dL/d(color-net output) given directly (then d_rgb / rgb are unused)
     __half* dys_out;         // [M,16] dL/d(sigma-net output)
+    // device-driven inference loop: the row count is read on the device (min(B, *rows_dev)); NULL = use the launch argument
+    const uint32_t* rows_dev;
 };
 
 // degree-4 real SH of one direction, fp32 (same recurrence as k_sh_forward<4>)
@@ -192,9 +194,10 @@ __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, b
 template <bool TRAIN, uint32_t ACT, int IN_MODE = IN_PLAIN, int OUT_MODE = OUT_PLAIN>
 __global__ void __launch_bounds__(128)
 k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ weights,
-                __half* __restrict__ forward_buffer, __half* __restrict__ outputs, const uint32_t B,
+                __half* __restrict__ forward_buffer, __half* __restrict__ outputs, const uint32_t B_arg,
                 const uint32_t in_dim, const uint32_t num_layers, const FieldArgs fa) {
     extern __shared__ unsigned char smem_dyn[];
+    const uint32_t B = fa.rows_dev ? min(B_arg, __ldg(fa.rows_dev)) : B_arg;
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ LevelParams lv[32];
@@ -1169,10 +1172,15 @@ extern "C" int ngp_ffmlp_wgrad_finalize(void* workspace, void* grad_weights, uin
 
 // ---- fused NeRF-field entry points (extensions: the reference has no single op for these; they replace
 // GridEncoder -> FFMLP -> trunc_exp and SHEncoder -> cat -> FFMLP -> sigmoid of nerf/network_ff.py:51-74) -------
-extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32_t* offsets, uint32_t L, float S,
-                                       uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
-                                       uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer,
-                                       void* h_out, float* sigma_out, ngp_stream_t stream) {
+static int field_sigma_forward_impl(const float* xyz, float bound, const uint32_t* rows_dev, const void* table_f16, const int32_t* offsets,
+                                    uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
+                                    uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer, void* h_out,
+                                    float* sigma_out, ngp_stream_t stream);
+
+static int field_sigma_forward_impl(const float* x01, float bound, const uint32_t* rows_dev, const void* table_f16, const int32_t* offsets,
+                                    uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
+                                    uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer, void* h_out,
+                                    float* sigma_out, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     const uint32_t in_dim = 2 * L;
     int rc = check_cfg("field_sigma_forward", M, in_dim, OUT_PAD, HID, num_layers, ACT_NONE);
@@ -1180,7 +1188,7 @@ extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, 
     if (L % 4 != 0 || L > 32) return fail(NGP_EUNSUPPORTED, "field_sigma_forward: L must be a multiple of 4, <= 32");
     if (train && (!forward_buffer || !feat_out)) return fail(NGP_EINVAL, "field_sigma_forward: training needs forward_buffer and feat_out");
     FieldArgs fa{};
-    fa.xyz = x01; fa.bound = 0.f; fa.inv_2bound = 1.f; fa.table = (const __half*)table_f16; fa.offsets = offsets; fa.L = L;
+    fa.xyz = x01; fa.bound = bound; fa.inv_2bound = bound > 0.f ? 1.0f / (2.0f * bound) : 1.f; fa.rows_dev = rows_dev; fa.table = (const __half*)table_f16; fa.offsets = offsets; fa.L = L;
     fa.S = S; fa.H = H; fa.gridtype = gridtype; fa.align_corners = align_corners; fa.feat_out = (__half*)feat_out;
     fa.sigma_out = sigma_out;
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
@@ -1208,18 +1216,49 @@ extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, 
     return check_launch("field_sigma_forward");
 }
 
+extern "C" int ngp_field_sigma_forward(const float* x01, const void* table_f16, const int32_t* offsets, uint32_t L, float S,
+                                       uint32_t H, uint32_t gridtype, int align_corners, const void* weights,
+                                       uint32_t num_layers, uint32_t M, int train, void* feat_out, void* forward_buffer,
+                                       void* h_out, float* sigma_out, ngp_stream_t stream) {
+    return field_sigma_forward_impl(x01, 0.f, nullptr, table_f16, offsets, L, S, H, gridtype, align_corners, weights, num_layers, M, train,
+                                    feat_out, forward_buffer, h_out, sigma_out, stream);
+}
+
+// Inference form for the device-driven render loop: xyz are WORLD coordinates in [-bound, bound] (GridEncoder.forward's affine map
+// (x + bound) / (2 bound) is applied in the kernel, same rounding as torch's), the number of valid rows is min(M_max, *rows_dev).
+extern "C" int ngp_field_sigma_forward_dev(const float* xyz, float bound, const uint32_t* rows_dev, const void* table_f16,
+                                           const int32_t* offsets, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                           int align_corners, const void* weights, uint32_t num_layers, uint32_t M_max, void* h_out,
+                                           float* sigma_out, ngp_stream_t stream) {
+    if (bound <= 0.f) return fail(NGP_EINVAL, "field_sigma_forward_dev: bound must be positive");
+    return field_sigma_forward_impl(xyz, bound, rows_dev, table_f16, offsets, L, S, H, gridtype, align_corners, weights, num_layers, M_max, 0,
+                                    nullptr, nullptr, h_out, sigma_out, stream);
+}
+
 // pad (nullable) [M] fp16 = the color net's last input column; h_out (nullable) [M,16] fp16 = pre-sigmoid network output.
 // rgb_out non-null: sigmoid epilogue (fused step); rgb_out null: plain FFMLP output into h_out (drop-in FFMLP path).
+static int field_color_forward_impl(const float* dirs, const void* h_sigma, const void* pad, const uint32_t* rows_dev, const void* weights,
+                                    uint32_t num_layers, uint32_t M, int train, void* forward_buffer, float* rgb_out,
+                                    void* h_out, ngp_stream_t stream);
 extern "C" int ngp_field_color_forward_ex(const float* dirs, const void* h_sigma, const void* pad, const void* weights,
                                           uint32_t num_layers, uint32_t M, int train, void* forward_buffer, float* rgb_out,
                                           void* h_out, ngp_stream_t stream) {
+    return field_color_forward_impl(dirs, h_sigma, pad, nullptr, weights, num_layers, M, train, forward_buffer, rgb_out, h_out, stream);
+}
+extern "C" int ngp_field_color_forward_dev(const float* dirs, const void* h_sigma, const uint32_t* rows_dev, const void* weights,
+                                           uint32_t num_layers, uint32_t M_max, float* rgb_out, ngp_stream_t stream) {
+    return field_color_forward_impl(dirs, h_sigma, nullptr, rows_dev, weights, num_layers, M_max, 0, nullptr, rgb_out, nullptr, stream);
+}
+static int field_color_forward_impl(const float* dirs, const void* h_sigma, const void* pad, const uint32_t* rows_dev, const void* weights,
+                                    uint32_t num_layers, uint32_t M, int train, void* forward_buffer, float* rgb_out,
+                                    void* h_out, ngp_stream_t stream) {
     if (M == 0) return NGP_OK;
     int rc = check_cfg("field_color_forward", M, 32, OUT_PAD, HID, num_layers, ACT_NONE);
     if (rc) return rc;
     if (train && !forward_buffer) return fail(NGP_EINVAL, "field_color_forward: training needs forward_buffer");
     if (!rgb_out && !h_out) return fail(NGP_EINVAL, "field_color_forward: no output requested");
     FieldArgs fa{};
-    fa.dirs = dirs; fa.h_sigma = (const __half*)h_sigma; fa.rgb_out = rgb_out; fa.pad = (const __half*)pad;
+    fa.dirs = dirs; fa.h_sigma = (const __half*)h_sigma; fa.rgb_out = rgb_out; fa.pad = (const __half*)pad; fa.rows_dev = rows_dev;
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
     const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, 4);
     cudaStream_t st = as_stream(stream);

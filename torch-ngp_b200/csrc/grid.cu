@@ -208,6 +208,10 @@ __device__ __forceinline__ void red_add_h4(__half* addr, __half2 lo, __half2 hi)
     const uint32_t a = *reinterpret_cast<const uint32_t*>(&lo), b = *reinterpret_cast<const uint32_t*>(&hi);
     asm volatile("red.global.add.noftz.v2.f16x2 [%0], {%1, %2};" ::"l"(addr), "r"(a), "r"(b) : "memory");
 }
+// four adjacent C == 2 half entries (one 16-byte aligned quad) in one reduction: REDG.E.ADD.F16x8
+__device__ __forceinline__ void red_add_h8(__half* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void red_add_f4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(512)
 k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 const int* __restrict__ offsets, T* __restrict__ grad_table, const uint32_t B,
                 const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
-                const bool align_corners, const uint32_t interp, const bool level_major) {
+                const bool align_corners, const uint32_t interp, const bool level_major, const bool quad_ok) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x;
     const uint32_t warp = threadIdx.y;
@@ -294,6 +298,10 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
         const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
         const bool issue = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
 
+        // vector reductions address relative to the level base: the level's first entry must itself be suitably aligned
+        // (always true for tables built by GridEncoder: offsets are multiples of 8 entries, grid.py:124)
+        const bool pair_lvl = (off & 1u) == 0u, quad_lvl = quad_ok && (off & 3u) == 0u;
+        (void)pair_lvl; (void)quad_lvl;
         if constexpr (C == 2) {
             // corners 2j and 2j+1 differ only in x.  When their entries are an aligned adjacent pair (dense level with an
             // even base index; hashed level with an even x) both are updated by ONE vector reduction (f16x4 / f32x4):
@@ -321,10 +329,19 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 }
                 if (issue) {
                     const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
-                    const bool pair = ((i0 ^ i1) == 1u);
+                    const bool pair = ((i0 ^ i1) == 1u) && pair_lvl;
                     if constexpr (sizeof(T) == 2) {
                         const __half2 h0 = __floats2half2_rn(v0[0], v0[1]), h1 = __floats2half2_rn(v1[0], v1[1]);
-                        if (pair) {
+                        if (quad_lvl && !pair && (i0 ^ i1) < 4u) {
+                            // x and x+1 fall into the same aligned quad of entries without being an aligned pair (x odd on a hashed
+                            // level: idx(x) ^ idx(x+1) = 3; dense level with idx % 4 == 1): one 16-byte reduction, the two untouched
+                            // entries receive +0.  Together with the pair case this covers 3 of 4 x-pairs with a single REDG.
+                            const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+                            const uint32_t a0 = i0 & 3u, a1 = i1 & 3u;
+                            red_add_h8(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~3u) * 2),
+                                       (a0 == 0u ? u0 : 0u) | (a1 == 0u ? u1 : 0u), (a0 == 1u ? u0 : 0u) | (a1 == 1u ? u1 : 0u),
+                                       (a0 == 2u ? u0 : 0u) | (a1 == 2u ? u1 : 0u), (a0 == 3u ? u0 : 0u) | (a1 == 3u ? u1 : 0u));
+                        } else if (pair) {
                             red_add_h4(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~1u) * 2), (i0 < i1) ? h0 : h1, (i0 < i1) ? h1 : h0);
                         } else {
                             red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i0 * 2), h0);
@@ -508,8 +525,10 @@ static int launch_bwd(const void* grad, const float* inputs, const int* offsets,
     const uint32_t nw = L < 16 ? L : 16;
     dim3 block(32, nw);
     dim3 grid(div_up(B, TILE_PTS));
+    // 16-byte vector reductions need a 16-byte aligned table (level offsets are multiples of 8 entries: grid.py:124)
+    const bool quad_ok = (reinterpret_cast<uintptr_t>(gemb) & 15u) == 0;
     k_grid_backward<T, D, C><<<grid, block, 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
-                                                     gridtype, ac, interp, level_major);
+                                                     gridtype, ac, interp, level_major, quad_ok);
     int rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && ginp) {

@@ -525,6 +525,128 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* __restr
     image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
 }
 
+// ---- device-driven inference loop (extension) ----------------------------------------------------------------------------
+// The reference's eval loop (renderer.py:337-367) reads n_alive back to the host every iteration (`rays_alive[rays_alive >= 0]`, a
+// boolean-index copy + synchronisation) to size the next launch.  Here the loop state lives in a device control block
+//   ctrl[0] = n_alive   ctrl[1] = n_step = max(min(N / n_alive, 8), 1)   ctrl[2] = M = n_alive * n_step rounded up to 128 (+128 when
+//   already a multiple, the wrapper's rule)   ctrl[3] = samples marched per ray so far (loop ends at max_steps)   ctrl[4] = scratch
+// and every kernel is launched for the worst case (N rays) and returns early past n_alive, so an iteration needs no host
+// round trip and a block of iterations can be captured in one CUDA graph.  Per-ray arithmetic is the kernels' above (same
+// march_probe / compositing sequence, same n_step schedule); only the ORDER of the compacted ray list differs (atomics), which no
+// per-ray result depends on.
+__global__ void k_infer_init(uint32_t N, int* __restrict__ rays_alive, uint32_t* __restrict__ ctrl) {
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n < N) rays_alive[n] = (int)n;
+    if (n == 0) {
+        ctrl[0] = N; ctrl[1] = 1u;
+        ctrl[2] = N + (128u - N % 128u);
+        ctrl[3] = 0u; ctrl[4] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_march_rays_dev(const uint32_t* __restrict__ ctrl, const int* __restrict__ rays_alive, const float* __restrict__ rays_t,
+                 const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, float dt_gamma,
+                 uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+                 const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                 const float* __restrict__ noises) {
+    const uint32_t n_alive = ctrl[0], n_step = ctrl[1];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    RayConst r;
+    ray_setup(r, rays_o + (size_t)index * 3, rays_d + (size_t)index * 3, bound, dt_gamma, max_steps, C, H);
+    float* __restrict__ px = xyzs + (size_t)n * n_step * 3;
+    float* __restrict__ pd = dirs + (size_t)n * n_step * 3;
+    float* __restrict__ pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    const float far = fars[index];
+    const float noise = (noises && ctrl[3] == 0u) ? noises[n] : 0.0f;      // perturb only in the first iteration (renderer.py:353)
+    t = fmaf(clampf(t * dt_gamma, r.dt_min, r.dt_max), noise, t);
+    float last_t = t, x, y, z, dt;
+    uint32_t step = 0;
+    while (t < far && step < n_step) {
+        if (march_probe(r, grid, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            pl[0] = dt; pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            step++;
+        }
+    }
+    // the reference zero-fills the buffers before every launch (raymarching.py:336-338); only the first unused delta matters (the
+    // compositor stops at delta == 0), so write that sentinel instead of clearing M rows
+    if (step < n_step) { pl[0] = 0.0f; pl[1] = 0.0f; }
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_rays_dev(const uint32_t* __restrict__ ctrl, float T_thresh, int* __restrict__ rays_alive, float* __restrict__ rays_t,
+                     const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                     float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n_alive = ctrl[0], n_step = ctrl[1];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    if (n >= n_alive) return;
+    const int index = rays_alive[n];
+    const float* __restrict__ sg = sigmas + (size_t)n * n_step;
+    const float* __restrict__ cl = rgbs + (size_t)n * n_step * 3;
+    const float* __restrict__ dl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[index];
+    float weight_sum = weights_sum[index], d = depth[index];
+    float r = image[index * 3], g = image[index * 3 + 1], b = image[index * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float d0 = dl[step * 2];
+        if (d0 == 0) break;
+        const float alpha = 1.0f - __expf(-sg[step] * d0);
+        const float T = 1 - weight_sum;
+        const float weight = alpha * T;
+        weight_sum += weight;
+        t += dl[step * 2 + 1];
+        d = fmaf(weight, t, d);
+        r = fmaf(weight, cl[step * 3], r);
+        g = fmaf(weight, cl[step * 3 + 1], g);
+        b = fmaf(weight, cl[step * 3 + 2], b);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else rays_t[index] = t;
+    weights_sum[index] = weight_sum;
+    depth[index] = d;
+    image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+}
+
+// survivors of rays_in[0 .. n_alive) -> rays_out (warp-aggregated slot reservation in ctrl[4])
+__global__ void __launch_bounds__(256)
+k_compact_rays_dev(uint32_t* __restrict__ ctrl, const int* __restrict__ rays_in, int* __restrict__ rays_out) {
+    const uint32_t n_alive = ctrl[0];
+    const uint32_t n = threadIdx.x + blockIdx.x * blockDim.x;
+    const int v = (n < n_alive) ? rays_in[n] : -1;
+    const bool keep = v >= 0;
+    const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(ctrl + 4, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) rays_out[base + __popc(mask & ((1u << lane) - 1u))] = v;
+}
+
+// next iteration's control block (one thread): n_alive = survivors, n_step = max(min(N / n_alive, 8), 1) (renderer.py:349)
+__global__ void k_infer_advance(uint32_t* __restrict__ ctrl, uint32_t N, uint32_t max_steps) {
+    const uint32_t steps_done = ctrl[3] + ctrl[1];
+    uint32_t alive = ctrl[4];
+    if (steps_done >= max_steps) alive = 0;                 // `while step < max_steps`
+    uint32_t n_step = 1;
+    if (alive > 0) { n_step = N / alive; n_step = n_step < 8u ? n_step : 8u; n_step = n_step > 1u ? n_step : 1u; }
+    const uint32_t m = alive * n_step;
+    ctrl[0] = alive; ctrl[1] = n_step;
+    ctrl[2] = alive ? m + (128u - m % 128u) : 0u;
+    ctrl[3] = steps_done; ctrl[4] = 0u;
+}
+
 }  // namespace ngp
 
 using namespace ngp;
@@ -594,4 +716,32 @@ extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thr
                                   float* weights_sum, float* depth, float* image, ngp_stream_t stream) {
     NGP_LAUNCH_1D(k_composite_rays, n_alive, 128, "composite_rays", n_alive, n_step, T_thresh, rays_alive, rays_t,
                   sigmas, rgbs, deltas, weights_sum, depth, image);
+}
+
+// ---- device-driven inference loop (extension; see the kernels' comment) ------------------------------------------------------------
+extern "C" int ngp_infer_init(uint32_t N, int32_t* rays_alive, uint32_t* ctrl, ngp_stream_t stream) {
+    if (N == 0) return fail(NGP_EINVAL, "infer_init: no rays");
+    NGP_LAUNCH_1D(k_infer_init, N, 256, "infer_init", N, rays_alive, ctrl);
+}
+extern "C" int ngp_march_rays_dev(const uint32_t* ctrl, uint32_t N, const int32_t* rays_alive, const float* rays_t,
+                                  const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                  uint32_t C, uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs,
+                                  float* deltas, const float* noises, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_march_rays_dev, N, 128, "march_rays_dev", ctrl, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps,
+                  C, H, grid, fars, xyzs, dirs, deltas, noises);
+}
+extern "C" int ngp_composite_rays_dev(const uint32_t* ctrl, uint32_t N, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                      const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                      float* depth, float* image, ngp_stream_t stream) {
+    NGP_LAUNCH_1D(k_composite_rays_dev, N, 128, "composite_rays_dev", ctrl, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
+                  weights_sum, depth, image);
+}
+extern "C" int ngp_compact_rays_dev(uint32_t* ctrl, uint32_t N, uint32_t max_steps, const int32_t* rays_in, int32_t* rays_out,
+                                    ngp_stream_t stream) {
+    if (N == 0) return NGP_OK;
+    k_compact_rays_dev<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(ctrl, rays_in, rays_out);
+    int rc = check_launch("compact_rays_dev");
+    if (rc) return rc;
+    k_infer_advance<<<1, 1, 0, as_stream(stream)>>>(ctrl, N, max_steps);
+    return check_launch("compact_rays_dev(advance)");
 }

@@ -194,7 +194,7 @@ class FusedTrainStep:
     Samples live in two persistent (ping-pong) buffer sets sized for the model's steady-state budget `mean_count`."""
 
     def __init__(self, model, optimizer, rays_total, bg_color=1.0, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, perturb=True,
-                 chunks=4, group=None, prefetch_point="start"):
+                 chunks=1, group=None, prefetch_point="start"):
         self.model, self.opt, self.R = model, optimizer, float(rays_total)
         self.bg, self.T_thresh, self.dt_gamma, self.max_steps, self.perturb = bg_color, T_thresh, dt_gamma, max_steps, perturb
         self.chunks, self.group = int(chunks), group
@@ -350,3 +350,121 @@ class FusedTrainStep:
         the next step's rays are marched in the background."""
         self._next = (next_rays_o, next_rays_d)
         return self.body(target)
+
+
+class EvalRenderer:
+    """Full-frame inference (the eval branch of nerf/renderer.py run_cuda, :323-372) without a host round trip per iteration.
+
+    Same kernels' arithmetic as the reference loop — march n_step samples per alive ray, evaluate the field, composite, drop finished
+    rays, n_step = max(min(N / n_alive, 8), 1) — but the loop state (n_alive, n_step, M) lives in a device control block, alive rays
+    are compacted on the device, the field is the fused inference pair (encoder -> sigma MLP -> exp ; SH + geo -> color MLP -> sigmoid,
+    affine map, trunc_exp and sigmoid inside the kernels), and `block` iterations are captured in ONE CUDA graph that is replayed
+    until the control block reports no alive rays (one 4-byte host read per block instead of a boolean-index sync per iteration)."""
+
+    def __init__(self, model, n_rays, block=8, T_thresh=1e-4, dt_gamma=0.0, max_steps=1024, use_graph=True):
+        self.m, self.N, self.block = model, int(n_rays), int(block)
+        self.T_thresh, self.dt_gamma, self.max_steps, self.use_graph = T_thresh, dt_gamma, max_steps, use_graph
+        dev = model.density_bitfield.device
+        N = self.N
+        Mmax = N + 128 + (128 - (N + 128) % 128)          # n_alive * n_step <= N, padded like the wrapper does
+        f = dict(dtype=torch.float32, device=dev)
+        self.ctrl = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.alive = [torch.empty(N, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.rays_o, self.rays_d = torch.empty(N, 3, **f), torch.empty(N, 3, **f)
+        self.nears, self.fars, self.rays_t = torch.empty(N, **f), torch.empty(N, **f), torch.empty(N, **f)
+        self.xyzs, self.dirs, self.deltas = torch.zeros(Mmax, 3, **f), torch.zeros(Mmax, 3, **f), torch.zeros(Mmax, 2, **f)
+        self.h = torch.empty(Mmax, 16, dtype=torch.half, device=dev)
+        self.sigma, self.rgb = torch.zeros(Mmax, **f), torch.zeros(Mmax, 3, **f)
+        self.wsum, self.depth, self.image = torch.empty(N, **f), torch.empty(N, **f), torch.empty(N, 3, **f)
+        self.Mmax = Mmax
+        self.graph = None
+        self.iterations = 0
+        if model.density_scale != 1:
+            raise RuntimeError("EvalRenderer: density_scale != 1 is not supported by the fused inference loop")
+
+    def _iteration(self, cur):
+        import _ngp_b200 as nb
+        from nerf_fused import field_cfg
+        from ngp_autograd import _half_table
+        m, N = self.m, self.N
+        enc = m.encoder
+        a_in, a_out = self.alive[cur], self.alive[1 - cur]
+        c = self.ctrl.data_ptr()
+        nb.call("ngp_march_rays_dev", c, N, a_in.data_ptr(), self.rays_t.data_ptr(), self.rays_o.data_ptr(), self.rays_d.data_ptr(),
+                float(m.bound), float(self.dt_gamma), int(self.max_steps), int(m.cascade), int(m.grid_size), m.density_bitfield.data_ptr(),
+                self.fars.data_ptr(), self.xyzs.data_ptr(), self.dirs.data_ptr(), self.deltas.data_ptr(), None)
+        nb.call("ngp_field_sigma_forward_dev", self.xyzs.data_ptr(), float(m.bound), c + 8, self._table.data_ptr(), enc.offsets.data_ptr(),
+                enc.offsets.shape[0] - 1, float(np.log2(enc.per_level_scale)), int(enc.base_resolution), enc.gridtype_id,
+                int(enc.align_corners), self._ws.data_ptr(), m.sigma_net.num_layers, self.Mmax, self.h.data_ptr(), self.sigma.data_ptr())
+        nb.call("ngp_field_color_forward_dev", self.dirs.data_ptr(), self.h.data_ptr(), c + 8, self._wc.data_ptr(), m.color_net.num_layers,
+                self.Mmax, self.rgb.data_ptr())
+        nb.call("ngp_composite_rays_dev", c, N, float(self.T_thresh), a_in.data_ptr(), self.rays_t.data_ptr(), self.sigma.data_ptr(),
+                self.rgb.data_ptr(), self.deltas.data_ptr(), self.wsum.data_ptr(), self.depth.data_ptr(), self.image.data_ptr())
+        nb.call("ngp_compact_rays_dev", c, N, int(self.max_steps), a_in.data_ptr(), a_out.data_ptr())
+
+    def _block(self):
+        for k in range(self.block):
+            self._iteration(k % 2)
+
+    @torch.no_grad()
+    def __call__(self, rays_o, rays_d, bg_color=1.0):
+        import _ngp_b200 as nb
+        from nerf_fused import field_cfg
+        from ngp_autograd import _half_table
+        m, N = self.m, self.N
+        assert self.block % 2 == 0, "an even block keeps the alive-list ping-pong aligned across replays"
+        field_cfg(m.encoder, m.sigma_net, m.color_net, m.bound, False)       # validates the topology
+        self.rays_o.copy_(rays_o.reshape(-1, 3)); self.rays_d.copy_(rays_d.reshape(-1, 3))
+        # weights may have changed since the last frame: refresh the fp16 operands in place (graph-stable addresses)
+        table = _half_table(m.encoder.embeddings)
+        if getattr(self, "_table", None) is None or self._table.shape != table.shape:
+            self._table = table.clone() if table is not getattr(m.encoder.embeddings, "_ngp_half_shadow", None) else table
+            self._ws = m.sigma_net.weights.detach().half().contiguous()
+            self._wc = m.color_net.weights.detach().half().contiguous()
+        else:
+            if self._table is not table:
+                self._table.copy_(table)
+            self._ws.copy_(m.sigma_net.weights.detach()); self._wc.copy_(m.color_net.weights.detach())
+        nb.call("ngp_near_far_from_aabb", self.rays_o.data_ptr(), self.rays_d.data_ptr(), m.aabb_train.data_ptr(), N, float(m.min_near),
+                self.nears.data_ptr(), self.fars.data_ptr())
+        self.rays_t.copy_(self.nears)
+        self.wsum.zero_(); self.depth.zero_(); self.image.zero_()
+        nb.call("ngp_infer_init", N, self.alive[0].data_ptr(), self.ctrl.data_ptr())
+        if self.use_graph and self.graph is None:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._block()                       # warm-up outside capture (kernel attribute calls, allocator)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            # the warm-up consumed real iterations: restart the frame
+            self.rays_t.copy_(self.nears); self.wsum.zero_(); self.depth.zero_(); self.image.zero_()
+            nb.call("ngp_infer_init", N, self.alive[0].data_ptr(), self.ctrl.data_ptr())
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._block()
+            # capture does not execute: the state is still the freshly initialised frame
+        self.iterations = 0
+        max_blocks = (self.max_steps + self.block - 1) // self.block + 1
+        for _ in range(max_blocks):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._block()
+            self.iterations += self.block
+            if int(self.ctrl[0].item()) == 0:        # the only host read: once per `block` iterations
+                break
+        image = self.image + (1 - self.wsum).unsqueeze(-1) * bg_color
+        depth = torch.clamp(self.depth - self.nears, min=0) / (self.fars - self.nears)
+        return {"image": image, "depth": depth, "weights_sum": self.wsum.clone()}
+
+
+def render_eval(model, rays_o, rays_d, bg_color=1.0, **kw):
+    """One-shot convenience wrapper (keeps one EvalRenderer per model / ray count)."""
+    n = rays_o.reshape(-1, 3).shape[0]
+    cache = model.__dict__.setdefault("_eval_renderers", {})
+    r = cache.get(n)
+    if r is None:
+        r = cache[n] = EvalRenderer(model, n, **kw)
+    return r(rays_o, rays_d, bg_color)

@@ -54,8 +54,10 @@ class Deferred(torch.Tensor):
         return torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=dtype, device=device, requires_grad=False)
 
     def materialize(self):
+        """The eager op, run under the autocast state the producing module saw (the consumer may sit outside the autocast region)."""
         if self._value is None:
-            self._value = self._compute()
+            with torch.autocast('cuda', dtype=torch.half, enabled=True):
+                self._value = self._compute()
         return self._value
 
     @classmethod
