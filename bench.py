@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--chunks", type=int, default=1, help="row chunks of the fused field (side-stream pipelining of color fwd / table scatter); 1 = off")
     ap.add_argument("--no-prefetch", action="store_true", help="march each step's rays inside that step instead of one step ahead on a low-priority stream")
     ap.add_argument("--prefetch-point", default="auto", choices=["auto", "start", "exchange"])
+    ap.add_argument("--mlp-backward", default="dual", choices=["dual", "single"], help="two-context MLP backward kernel (default) or the single-context one")
     ap.add_argument("--long-steps", type=int, default=200, help="extra, longer timed region reported as `long_run` (0 = skip)")
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c5", "infer"], help="BASELINE.json config: c2 = training step (default; c4 = the same under torchrun), c1 = GridEncoder fwd/bwd 64k points, c3 = fused density inference 4096x1024, c5 = SDF 1M points, infer = full-frame eval render")
     return ap.parse_args()
@@ -268,7 +269,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import _ngp_b200 as nb
     import ngp_dp
-    nb.load()
+    nb.load().ngp_debug_set_mlp_backward(1 if args.mlp_backward == "dual" else 0)
 
     R = args.rays_per_step
     n_local = int(ngp_dp.shard_indices(R, rank, world).numel())
@@ -593,6 +594,7 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "kernel_time_share": kern_ms / ms_eager, "kernels": breakdown,
             "cuda_graph": graphs is not None, "ms_per_step_eager_unpipelined": ms_eager / args.steps,
+            "mlp_backward_kernel": args.mlp_backward,
             "pipelining": {"field_chunks": args.chunks if use_fused_opt else 1, "march_prefetch": bool(prefetch),
                            "prefetch_point": (fstep.prefetch_point if fstep is not None else None),
                            "note": "per-kernel figures (`kernels`, `roofline`) come from an eager pass with the pipelining switched off, so that each launch is timed alone; the headline is the pipelined, graph-replayed step"},

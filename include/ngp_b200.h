@@ -283,6 +283,9 @@ int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);
+/* MLP backward kernel selection: 1 = two tile contexts per CTA with a deep activation ring (default, where it fits), 0 = the
+ * single-context kernel */
+int ngp_debug_set_mlp_backward(int dual);
 
 #ifdef __cplusplus
 }

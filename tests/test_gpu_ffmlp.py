@@ -289,3 +289,40 @@ def test_errors():
     x, w = _mk(128, 32, 2)
     with pytest.raises(RuntimeError):
         ffmlp_forward(x.cuda(), w.cuda(), 32, 16, 128, 2, 0, 6, True, False)      # hidden 128: not in this build
+
+
+@pytest.mark.parametrize("B", [77, 128, 128 * 3 + 5, 128 * 1201 + 64])
+@pytest.mark.parametrize("cfg", [dict(input_dim=32, num_layers=2), dict(input_dim=32, num_layers=3), dict(input_dim=64, num_layers=2)])
+def test_dual_context_backward_equals_single_context(cfg, B):
+    """k_ffmlp_backward_dual (two tile contexts per CTA, activation ring) against k_ffmlp_backward_fused on the same inputs: identical
+    dX (same per-tile arithmetic), weight gradients equal up to the fp32 summation order over tiles.  Sizes cover one ragged tile (the
+    second context idle), an odd tile count and a many-tiles-per-context run; with and without the input-gradient round."""
+    import _ngp_b200 as nb
+    lib = nb.load()
+    x, w = _mk(B, **cfg)
+    nl, ind = cfg["num_layers"], cfg["input_dim"]
+    xd, wd = x.cuda(), w.cuda()
+    fb = torch.empty(nl, B, 64, dtype=torch.half, device="cuda"); y = torch.empty(B, 16, dtype=torch.half, device="cuda")
+    nb.call("ngp_ffmlp_forward", xd.data_ptr(), wd.data_ptr(), B, ind, 16, 64, nl, 0, 6, fb.data_ptr(), y.data_ptr())
+    g = (torch.randn(B, 16, generator=gen(5)) * 0.1).half().cuda()
+    nbytes = lib.ngp_ffmlp_backward_workspace_bytes(B, ind, 16, 64, nl)
+    res = {}
+    try:
+        for dual in (0, 1):
+            lib.ngp_debug_set_mlp_backward(dual)
+            for calc_gi in (0, 1):
+                ws = torch.empty(nbytes // 4, device="cuda"); gw = torch.zeros_like(wd)
+                gi = torch.zeros(B, ind, dtype=torch.half, device="cuda")
+                nb.call("ngp_ffmlp_backward", g.data_ptr(), xd.data_ptr(), wd.data_ptr(), fb.data_ptr(), B, ind, 16, 64, nl, 0, 6, calc_gi,
+                        None, gi.data_ptr() if calc_gi else None, gw.data_ptr(), ws.data_ptr(), nbytes)
+                torch.cuda.synchronize()
+                res[(dual, calc_gi)] = (gi.clone(), ws.clone(), gw.clone())
+    finally:
+        lib.ngp_debug_set_mlp_backward(1)
+    for calc_gi in (0, 1):
+        gi0, ws0, gw0 = res[(0, calc_gi)]
+        gi1, ws1, gw1 = res[(1, calc_gi)]
+        if calc_gi:
+            assert torch.equal(gi0, gi1)
+        assert rel_err(ws1.cpu().numpy(), ws0.cpu().numpy()) < 1e-5
+        assert rel_err(gw1.float().cpu().numpy(), gw0.float().cpu().numpy()) < 1e-3

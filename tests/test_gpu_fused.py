@@ -74,3 +74,40 @@ def test_fused_train_step_runs_and_matches_loss():
     assert abs(la.item() - lb.item()) < 1e-4 * max(1.0, abs(la.item()))
     ga, gb = a.encoder.embeddings.grad, b.encoder.embeddings.grad
     assert float((ga - gb).norm() / ga.norm()) < 3e-2
+
+
+@pytest.mark.parametrize("M", [100, 128 * 2, 128 * 777 + 33])
+def test_color_backward_dual_equals_single(M):
+    """ngp_field_color_backward through the two-context kernel == through the single-context kernel (both output-gradient forms)."""
+    import _ngp_b200 as nb
+    lib = nb.load()
+    a, _ = _models()
+    d = torch.randn(M, 3, generator=gen(2)); d = (d / d.norm(dim=-1, keepdim=True)).cuda()
+    h = (torch.randn(M, 16, generator=gen(3)) * 0.5).half().cuda()
+    wc = a.color_net.weights.detach().half()
+    nl = a.color_net.num_layers
+    fb = torch.empty(nl, M, 64, dtype=torch.half, device="cuda"); rgb = torch.empty(M, 3, device="cuda")
+    nb.call("ngp_field_color_forward", d.data_ptr(), h.data_ptr(), wc.data_ptr(), nl, M, 1, fb.data_ptr(), rgb.data_ptr())
+    d_rgb = torch.randn(M, 3, generator=gen(4)).cuda(); d_sig = torch.randn(M, generator=gen(5)).cuda() * 0.1
+    g3 = (torch.randn(M, 3, generator=gen(6)) * 0.1).half().cuda()
+    nbytes = lib.ngp_ffmlp_backward_workspace_bytes(M, 32, 16, 64, nl)
+    res = {}
+    try:
+        for dual in (0, 1):
+            lib.ngp_debug_set_mlp_backward(dual)
+            for form in ("rgb", "grad_h"):
+                dys = torch.zeros(M, 16, dtype=torch.half, device="cuda"); gw = torch.zeros_like(wc); ws = torch.empty(nbytes // 4, device="cuda")
+                if form == "rgb":
+                    nb.call("ngp_field_color_backward", d_rgb.data_ptr(), rgb.data_ptr(), d_sig.data_ptr(), h.data_ptr(), d.data_ptr(), wc.data_ptr(),
+                            fb.data_ptr(), nl, M, dys.data_ptr(), gw.data_ptr(), ws.data_ptr(), nbytes)
+                else:
+                    nb.call("ngp_field_color_backward_ex", None, None, g3.data_ptr(), None, h.data_ptr(), d.data_ptr(), None, wc.data_ptr(),
+                            fb.data_ptr(), nl, M, dys.data_ptr(), gw.data_ptr(), ws.data_ptr(), nbytes, 0)
+                torch.cuda.synchronize()
+                res[(dual, form)] = (dys.clone(), ws.clone())
+    finally:
+        lib.ngp_debug_set_mlp_backward(1)
+    for form in ("rgb", "grad_h"):
+        assert torch.equal(res[(0, form)][0], res[(1, form)][0])
+        assert rel_err(res[(1, form)][1].cpu().numpy(), res[(0, form)][1].cpu().numpy()) < 1e-5
+        assert float(res[(1, form)][0].float().abs().sum()) > 0

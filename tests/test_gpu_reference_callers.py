@@ -158,3 +158,32 @@ def test_reference_update_extra_state_parity(warm):
     flips = int(np.unpackbits((ba ^ bb).cpu().numpy()).sum())
     assert flips < (5e-2 if warm else 1e-3) * 128 ** 3          # threshold crossings of near-threshold cells (+ duplicate draws when warm)
     print(f"update_extra_state(warm={warm}): grid rel err {rel_err(da, db):.2e}, mean {ma:.5f} vs {mb:.5f}, bit flips {flips}")
+
+
+@needs_stacks
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_device_driven_eval_loop_matches_the_reference_loop(use_graph):
+    """nerf_step.EvalRenderer (device-side alive-ray compaction, fused inference field, block of iterations in one CUDA graph) against
+    the reference's own run_cuda eval loop (renderer.py:323-372) over the drop-in packages: same image / depth / weights_sum."""
+    from nerf_step import NeRFFieldFF, EvalRenderer
+    N = 20000
+    rays_o, rays_d, _, _ = synth_rays(N, seed=2)
+    ro, rd = rays_o.cuda(), rays_d.cuda()
+    ours, ref, a, b = _twin_models()
+    torch.manual_seed(1)
+    f = NeRFFieldFF(bound=1).cuda().eval()
+    f.load_state_dict(a.state_dict(), strict=False)
+    with ours.active():
+        a.eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            want = a.render(ro[None], rd[None], staged=True, bg_color=1, perturb=False, dt_gamma=0, max_steps=1024)
+    er = EvalRenderer(f, N, use_graph=use_graph)
+    got = er(ro, rd, bg_color=1.0)
+    got2 = er(ro, rd, bg_color=1.0)                                       # a second frame through the same (captured) loop
+    wi, gi = want["image"][0].float().cpu().numpy(), got["image"].float().cpu().numpy()
+    assert np.abs(wi - gi).max() < 2e-3 and np.abs(wi - gi).mean() < 1e-4
+    assert torch.equal(got["image"], got2["image"])
+    wd, gd = want["depth"][0].float().cpu().numpy(), got["depth"].float().cpu().numpy()
+    assert np.array_equal(np.isnan(wd), np.isnan(gd)) and np.nanmax(np.abs(wd - gd)) < 2e-3
+    assert er.iterations >= 8 and er.iterations % 8 == 0
+    print(f"EvalRenderer(graph={use_graph}): {er.iterations} iterations, |dimg|max={np.abs(wi - gi).max():.2e}")

@@ -66,7 +66,7 @@ _SIGNATURES = {
     "ngp_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 # every symbol include/ngp_b200.h declares (tests check the .so exports all of them)
-EXPORTED = sorted(list(_SIGNATURES) + ["ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
+EXPORTED = sorted(list(_SIGNATURES) + ["ngp_debug_set_mlp_backward", "ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
                                        "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes",
                                        "ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"])
 
@@ -92,6 +92,8 @@ def load():
     lib.ngp_version.restype = _c.c_int
     lib.ngp_launch_count.restype = _c.c_uint64
     lib.ngp_reset_launch_count.restype = None
+    lib.ngp_debug_set_mlp_backward.argtypes = [_i32]
+    lib.ngp_debug_set_mlp_backward.restype = _c.c_int
     lib.ngp_ffmlp_backward_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32, _u32]
     lib.ngp_ffmlp_backward_workspace_bytes.restype = _sz
     for name in ("ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"):

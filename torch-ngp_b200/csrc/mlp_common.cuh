@@ -74,6 +74,35 @@ __device__ __forceinline__ void load_tile_rowmajor_async(uint32_t tile_addr, con
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// same copy without the commit: the caller groups several tiles / commits (possibly empty) groups itself
+__device__ __forceinline__ void load_tile_rowmajor_async_nocommit(uint32_t tile_addr, const __half* __restrict__ src, uint32_t rows,
+                                                                  uint32_t cols, uint32_t tid, uint32_t nthr, uint32_t rows_valid) {
+    const uint32_t cpr = cols >> 3;
+    const uint32_t total = rows * cpr;
+    for (uint32_t g = tid; g < total; g += nthr) {
+        const uint32_t r = g / cpr, c = g - r * cpr;
+        const bool ok = r < rows_valid;
+        const void* gp = reinterpret_cast<const uint4*>(src + (size_t)(ok ? r : 0) * cols) + c;
+        const uint32_t nbytes = ok ? 16u : 0u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_addr + sw128_off(r, c)), "l"(gp), "r"(nbytes) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `n` of this thread's most recent cp.async groups are still in flight (n is a run-time value <= 7)
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+// 128-thread named barrier (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync_128(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // zero-fill chunks [c0, 8) of every row of a tile
 __device__ __forceinline__ void zero_tile_cols(uint32_t tile_addr, uint32_t rows, uint32_t c0, uint32_t tid, uint32_t nthr) {
