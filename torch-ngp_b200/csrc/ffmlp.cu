@@ -853,7 +853,7 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
                       const __half* __restrict__ forward_buffer, __half* __restrict__ grad_inputs, float* __restrict__ wgrad_ws,
                       const uint32_t B, const uint32_t in_dim, const uint32_t num_layers, const FieldArgs fa) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[4];
     __shared__ uint32_t tmem_base_s;
 
     const uint32_t tid = threadIdx.x, ctx = tid >> 7, ltid = tid & 127u, lwarp = ltid >> 5, lane = tid & 31u;
@@ -869,10 +869,11 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
     const uint32_t g1_addr = c_base + A_TILE_BYTES;             // G0 at c_base, G1 right behind it
     const uint32_t f_base = c_base + 2u * A_TILE_BYTES;         // ring buffer j at f_base + j * 16 KB
     const uint32_t x_addr = f_base + num_layers * A_TILE_BYTES;
-    uint64_t* bar = &bars[ctx];
+    uint64_t* bar = &bars[ctx];            // per round: this round's dgrad (and everything issued before it) is complete
+    uint64_t* bar_w = &bars[2 + ctx];      // per tile: the tile's last weight-gradient MMAs are complete
     const uint32_t bar_id = 1u + ctx;
 
-    if (ltid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (ltid == 0) { mbar_init(bar, 1); mbar_init(bar_w, 1); mbar_fence_init(); }
     if (tid < 32) tmem_alloc<512>(&tmem_base_s);
     {   // transposed weights in consumption order, one copy for both contexts
         const __half* w0 = weights;
@@ -893,7 +894,7 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
     const uint32_t t_lane = tmem_ctx + ((lwarp * 32u) << 16);
     auto acc_addr = [&](uint32_t l) { return tmem_ctx + 64u + 64u * (l >> 1) + ((16u * (l & 1u)) << 16); };
     auto g_addr = [&](uint32_t i) { return c_base + (i & 1u) * A_TILE_BYTES; };
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase_w = 0;
     bool first_tile = true;
 
     const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
@@ -998,32 +999,35 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
 
         for (uint32_t r = 0; r < nrounds; ++r) {
             const bool to_inputs = want_dx && (r == nrounds - 1);
+            const bool last_round = (r == nrounds - 1);
             const uint32_t K = (r == 0) ? OUT_PAD : HID;
             const uint32_t N = to_inputs ? in_dim : HID;
             const uint32_t a_in = (r == 0) ? g1_addr : g_addr(r - 1);
+            // ring buffer r of THIS tile (H for this round's mask and weight gradient; X in the input-gradient round) has landed:
+            // groups committed after it = (num_layers - r) of this tile + (r - 1) refills for the next tile.  Waiting here lets ONE
+            // barrier publish both the previous epilogue's dPre tile and the copied tile.
+            cp_async_wait_pending(r == 0 ? num_layers : num_layers - 1);
             fence_async_smem();
             fence_before_sync();
             bar_sync_128(bar_id);
             if (lwarp == 0) {
                 if (ltid == 0) {
                     fence_after_sync();
-                    // weight gradient of the matmul consumed in the PREVIOUS round: its dPre tile and its H tile (ring buffer r-1) are complete
-                    if (r == 1) issue_wgrad(acc_addr(nmat - 1), g1_addr, f_base, first_tile ? 0u : 1u);
-                    else if (r >= 2) issue_wgrad(acc_addr(num_layers + 1 - r), g_addr(r - 2), f_base + (r - 1) * A_TILE_BYTES, first_tile ? 0u : 1u);
+                    // dgrad first and committed on its own: the epilogue below needs only this result ...
                     issue_layer(tmem_ctx, a_in, w_addr + r * W_SLOT_BYTES, N, K);
                     mma_commit(bar);
+                    // ... while the weight gradient of the SAME matmul (P = this round's input gradient tile, Q = ring buffer r) runs
+                    // underneath it.  tcgen05.mma executes in issue order, so the next round's commit also covers these.
+                    if (r == 0) issue_wgrad(acc_addr(nmat - 1), g1_addr, f_base, first_tile ? 0u : 1u);
+                    else issue_wgrad(acc_addr(num_layers - r), a_in, f_base + r * A_TILE_BYTES, first_tile ? 0u : 1u);
+                    if (last_round && want_dx) mma_commit(bar_w);
                 }
                 __syncwarp();
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
             fence_after_sync();
-            // ring buffer r-1 (last read by the wgrad just completed) takes the NEXT tile's activation tile
-            if (r >= 1) issue_load(next_tile, r - 1);
             if (!to_inputs) {
-                // buffer r of THIS tile: groups committed after it = (num_layers - r) of this tile + r refills for the next tile
-                cp_async_wait_pending(num_layers);
-                bar_sync_128(bar_id);
                 const uint32_t gw = g_addr(r), fw = f_base + r * A_TILE_BYTES;
 #pragma unroll
                 for (uint32_t half_i = 0; half_i < 2; ++half_i) {
@@ -1075,33 +1079,31 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
                     }
                 }
             }
+            // ring buffer r-1: its last reader (the previous round's weight gradient) completed before this round's dgrad did;
+            // it takes the NEXT tile's activation tile.  Issued after the epilogue so the copies' issue slots are off the round's chain.
+            if (r >= 1) issue_load(next_tile, r - 1);
         }
 
-        // tile tail: weight gradient of matmul 0 (P = dPre_0 in G[n_hidden & 1], Q = X) and, without an input-gradient round, of matmul 1
-        {
-            if constexpr (!FIELD_COLOR) cp_async_wait_pending(nrounds - 1);     // X of this tile: (nrounds - 1) next-tile refills came after it
+        // tile tail: without an input-gradient round the weight gradient of matmul 0 (P = dPre_0, Q = X) still has to be issued
+        if (!want_dx) {
+            cp_async_wait_pending(num_layers - 1);          // X of this tile
             fence_async_smem();
             fence_before_sync();
             bar_sync_128(bar_id);
             if (lwarp == 0) {
                 if (ltid == 0) {
                     fence_after_sync();
-                    if (!want_dx) {
-                        const uint32_t r = nrounds;   // == 1 + n_hidden: the wgrad the absent input round would have issued
-                        if (r == 1) issue_wgrad(acc_addr(nmat - 1), g1_addr, f_base, first_tile ? 0u : 1u);
-                        else issue_wgrad(acc_addr(num_layers + 1 - r), g_addr(r - 2), f_base + (r - 1) * A_TILE_BYTES, first_tile ? 0u : 1u);
-                    }
                     issue_wgrad(acc_addr(0), g_addr(n_hidden), x_addr, first_tile ? 0u : 1u);
-                    mma_commit(bar);
+                    mma_commit(bar_w);
                 }
                 __syncwarp();
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            fence_after_sync();
-            // the remaining ring buffers of the next tile (those whose last reader was this tail)
-            for (uint32_t j = nrounds - 1; j < nbuf; ++j) issue_load(next_tile, j);
         }
+        // every MMA of this tile has completed (dPre tiles, X and the ring buffers still referenced are free again)
+        mbar_wait(bar_w, phase_w);
+        phase_w ^= 1u;
+        fence_after_sync();
+        for (uint32_t j = nrounds - 1; j < nbuf; ++j) issue_load(next_tile, j);
         first_tile = false;
     }
     cp_async_wait_all();

@@ -9,6 +9,7 @@ It is host glue, not a kernel; bench.py drives it, tests check it against the or
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
 
