@@ -566,12 +566,14 @@ def main():
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"], "unit": "GB/s", "frac": ach_gb / pk["hbm"],
                 "tensor_tflops": ach_tf or None}
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath)).get(dom)
         if t:   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, scaled per sample to this launch
             traffic = t["dram_bytes_per_sample"] * dd["units"] / dd["calls"]
-    roof.update({"traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full, per-sample x samples/launch)" if traffic else None,
+    roof.update({"traffic": traffic, "traffic_source": (os.path.relpath(tpath, ROOT) + " (ncu --set full, per-sample x samples/launch)") if traffic else None,
                  "peak_source": pk["src"], "avg_launch_ms": per_launch_ms,
                  "share_of_step": dd["ms"] / ms_eager, "algorithmic_bytes_per_launch": dd["bytes"] / dd["calls"]})
     launches = launches // 1      # launches of OUR kernels per timed region (counted in the eager pass; a graph replays the same set)
@@ -599,6 +601,37 @@ def main():
                            "prefetch_point": (fstep.prefetch_point if fstep is not None else None),
                            "note": "per-kernel figures (`kernels`, `roofline`) come from an eager pass with the pipelining switched off, so that each launch is timed alone; the headline is the pipelined, graph-replayed step"},
             "long_run": long_run, "timed_region_s": ms_total * 1e-3}
+
+    # ---- the table scatter is an L2-reduction kernel (the fp16 gradient table is L2-resident: dram traffic is 0.18x the algorithmic
+    # bytes): report it against the device's MEASURED reduction rate for the same access pattern as well (random f16x2 / v2.f16x2
+    # reductions into a 24.5 MB table, ngp_debug_red_probe), next to the HBM fraction the contract asks for
+    try:
+        n_entries = int(model.encoder.embeddings.shape[0]) // 4 * 4
+        probe_tab = torch.zeros(n_entries, 2, dtype=torch.half, device=dev)
+        blocks, ops = 148 * 16, 128
+        rates = {}
+        for mode, nm in ((0, "f16x2_4B"), (1, "v2_f16x2_8B")):
+            for rep in range(2):
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                nb.call("ngp_debug_red_probe", probe_tab.data_ptr(), n_entries, blocks, ops, mode)
+                b.record()
+                torch.cuda.synchronize()
+            rates[nm] = blocks * 256 * ops / (a.elapsed_time(b) * 1e-3) / 1e9
+        red_per_sample = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get("ngp_grid_encode_backward", {}).get("red_ops_per_sample") \
+            if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else None
+        gb = agg.get("ngp_grid_encode_backward")
+        line_red = {"peak_gops_measured": rates, "how": "ngp_debug_red_probe: 148*16 blocks x 256 threads x 128 random-entry reductions into a 24.5 MB fp16x2 table"}
+        if red_per_sample and gb:
+            ops_per_launch = red_per_sample * gb["units"] / gb["calls"]
+            ach = ops_per_launch / (gb["ms"] / gb["calls"] * 1e-3) / 1e9
+            line_red.update({"kernel": "ngp_grid_encode_backward", "red_ops_per_sample": red_per_sample, "achieved_gops": ach,
+                             "frac_of_measured_8B_rate": ach / rates["v2_f16x2_8B"],
+                             "source": "red ops per sample = lts__t_sectors_srcunit_tex_op_red.sum / rows of the ncu --set full capture (profiles/r2_ncu_step.md)"})
+        line["l2_reduction_roofline"] = line_red
+        del probe_tab
+    except Exception as e:
+        line["l2_reduction_roofline"] = {"unavailable": str(e)[:200]}
 
     # side arms run in child processes with hard timeouts: a reported baseline must never cost the bench line
     def child(cmd, timeout):

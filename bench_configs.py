@@ -75,8 +75,12 @@ def _cores():
 
 
 def _finish(line, args):
-    import bench
-    bench.emit(line)
+    main_mod = sys.modules.get("__main__")
+    emit = getattr(main_mod, "emit", None)          # bench.py run as a script owns the saved stdout descriptor
+    if emit is None:
+        import bench
+        emit = bench.emit
+    emit(line)
 
 
 # ================================================================================================ C1

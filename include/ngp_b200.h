@@ -283,6 +283,9 @@ int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B
 /* test hooks (not part of the reference ABI) */
 int ngp_grid_level_scales(float* out_device, uint32_t L, float S, uint32_t H, ngp_stream_t stream);
 int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream);
+/* L2 reduction-rate probe: blocks x 256 threads x ops_per_thread reductions at pseudo-random entries of table[entries] (f16x2 entries);
+ * mode 0 = 4-byte f16x2, 1 = 8-byte v2.f16x2, 2 = 16-byte v4.f16x2.  The ceiling the table scatter is reported against. */
+int ngp_debug_red_probe(void* table_f16x2, uint32_t entries, uint32_t blocks, uint32_t ops_per_thread, int mode, ngp_stream_t stream);
 /* MLP backward kernel selection: 1 = two tile contexts per CTA with a deep activation ring (default, where it fits), 0 = the
  * single-context kernel */
 int ngp_debug_set_mlp_backward(int dual);

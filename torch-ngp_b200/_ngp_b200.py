@@ -42,6 +42,7 @@ _SIGNATURES = {
     "ngp_field_sigma_forward_dev": [_vp, _f32, _vp, _vp, _vp, _u32, _f32, _u32, _u32, _i32, _vp, _u32, _u32, _vp, _vp, _vp],
     "ngp_field_color_forward_dev": [_vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp],
     "ngp_debug_umma": [_vp, _vp, _vp, _i32, _vp],
+    "ngp_debug_red_probe": [_vp, _u32, _u32, _u32, _i32, _vp],
     "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
     "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],
     "ngp_optim_scaler_update": [_vp, _f32, _f32, _i32, _vp],

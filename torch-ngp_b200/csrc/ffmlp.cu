@@ -832,31 +832,58 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
     if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
-// ================================ backward: fused dgrad + wgrad, two tile contexts per CTA ==========================
-// Same mathematics, operand layouts and TMEM accumulator scheme as k_ffmlp_backward_fused, restructured around what bounds that
-// kernel (ncu r1: 50-62 % of its stall samples are long-scoreboard waits, tensor pipe 11 %): every round waited for a 16 KB
-// forward-activation tile requested at the START of the same round, i.e. one HBM latency per round sat on the critical path with
-// only two tiles in flight per SM, and deeper prefetch did not fit (two CTAs x 107 KB of shared memory).  Here ONE 256-thread CTA
-// per SM runs two independent tile contexts (warpgroup = context: own dPre ping-pong tiles, own activation ring, own mbarrier,
-// own named barrier, own TMEM columns) that SHARE one copy of the transposed weights, packed to their exact sizes.  The shared
-// memory this frees holds a ring of num_layers + 1 activation tiles per context, refilled as soon as a buffer's last reader has
-// completed: every tile the backward needs (all H_l and X) is requested a whole 128-row tile (num_layers + 1 rounds) ahead of
-// its use, so no round waits on HBM.  Contexts never synchronise with each other inside the tile loop.
+// ================================ backward: fused dgrad + wgrad, warp-specialised, two tile contexts per CTA =========
+// Same mathematics, operand layouts and TMEM accumulator scheme as k_ffmlp_backward_fused, restructured around what bounded that
+// kernel (ncu r1: long-scoreboard waits 50-62 %, tensor pipe 11 %, 2 x 4 warps per SM):
+//   * one CTA per SM runs TWO independent tile contexts that share one copy of the transposed weights (packed to their exact
+//     sizes); the shared memory this frees holds, per context, a ring of num_layers + 1 activation tiles that is refilled as soon as a
+//     buffer's last reader has completed, so every H_l / X tile is requested a whole 128-row tile ahead of its use (no round waits
+//     on HBM any more: ncu r2 long_scoreboard 18 %);
+//   * warp specialisation: per context one MMA-ISSUE warp and a 128-thread EPILOGUE warpgroup (thread = batch row), coupled only by
+//     mbarriers — `ready` (128 epilogue arrivals: "the dPre tile of this round is in shared memory, the ring buffer has landed, my TMEM
+//     reads are done") and `done` (tcgen05.commit: "this round's dgrad has completed").  No bar.sync / __syncthreads inside the tile
+//     loop; the issuing lane no longer delays the epilogue warp it used to belong to (ncu r2a: 18 % of the stall samples sat behind
+//     the named barrier waiting for that warp);
+//   * the weight gradient of a matmul is issued in the SAME round right after its dgrad (P = the round's input-gradient tile, Q = ring
+//     buffer r) and runs under the epilogue; tcgen05.mma executes in issue order, so the next round's commit also covers it;
+//   * ReLU epilogue on packed halves: cvt.rn.f16x2 of the accumulator pair AND the H > 0 lane mask (3 instead of 7 instructions per
+//     pair: the epilogue is issue-bound at 8 epilogue warps per SM).
 //   shared memory: [W^T slots: (1 + n_hidden) x 8 KB + in_dim x 128 B] + 2 x [G0 G1 | F_0 .. F_nl] x 16 KB  (NeRF color net: 220 KB)
-//   TMEM (512 columns, one CTA per SM): context c owns columns [256 c, 256 c + 256): dgrad accumulator + weight-gradient
-//   accumulators exactly as in the single-context kernel.
-//   cp.async groups: every ring refill is one commit group per thread, committed in (tile, buffer) order — also when a context has
-//   no next tile (empty group) — so "buffer j of the current tile has landed" is a constant wait_group distance.
+//   TMEM (512 columns, one CTA per SM): context c owns columns [256 c, 256 c + 256): dgrad accumulator + weight-gradient accumulators.
+//   cp.async groups: every ring refill is one commit group per epilogue thread, committed in (tile, buffer) order — also when there is
+//   nothing to copy — so "buffer r of the current tile has landed" is a fixed wait_group distance.
+static constexpr uint32_t DUAL_THREADS = 2 * 128 + 2 * 32;
+
+template <uint32_t ACT>
+__device__ __forceinline__ void dpre_pack16(const uint32_t (&v)[32], const uint4 (&f)[4], uint32_t (&p)[16]) {
+    const __half2* fh = reinterpret_cast<const __half2*>(f);
+    if constexpr (ACT == ACT_RELU) {
+        const __half2 zero = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i)
+            p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])) & __hgt2_mask(fh[i], zero);
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i) {
+            const float2 ff = __half22float2(fh[i]);
+            p[i] = pack_h2(act_bwd<ACT>(__uint_as_float(v[2 * i]), ff.x), act_bwd<ACT>(__uint_as_float(v[2 * i + 1]), ff.y));
+        }
+    }
+}
+
 template <uint32_t ACT, bool FIELD_COLOR>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(DUAL_THREADS, 1)
 k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict__ inputs, const __half* __restrict__ weights,
                       const __half* __restrict__ forward_buffer, __half* __restrict__ grad_inputs, float* __restrict__ wgrad_ws,
                       const uint32_t B, const uint32_t in_dim, const uint32_t num_layers, const FieldArgs fa) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bars[4];
+    __shared__ __align__(8) uint64_t bars[6];
     __shared__ uint32_t tmem_base_s;
 
-    const uint32_t tid = threadIdx.x, ctx = tid >> 7, ltid = tid & 127u, lwarp = ltid >> 5, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const bool is_mma = tid >= 256;
+    const uint32_t ctx = is_mma ? ((tid - 256) >> 5) : (tid >> 7);
+    const uint32_t ltid = tid & 127u, lwarp = ltid >> 5;            // epilogue threads only
     const uint32_t base = align1024(smem_u32(smem_dyn));
     unsigned char* base_gen = smem_dyn + (base - smem_u32(smem_dyn));
     const uint32_t n_hidden = num_layers - 1;
@@ -869,265 +896,271 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
     const uint32_t g1_addr = c_base + A_TILE_BYTES;             // G0 at c_base, G1 right behind it
     const uint32_t f_base = c_base + 2u * A_TILE_BYTES;         // ring buffer j at f_base + j * 16 KB
     const uint32_t x_addr = f_base + num_layers * A_TILE_BYTES;
-    uint64_t* bar = &bars[ctx];            // per round: this round's dgrad (and everything issued before it) is complete
-    uint64_t* bar_w = &bars[2 + ctx];      // per tile: the tile's last weight-gradient MMAs are complete
-    const uint32_t bar_id = 1u + ctx;
+    uint64_t* bar_ready = &bars[ctx];       // epilogue -> MMA warp, 128 arrivals per round
+    uint64_t* bar_done = &bars[2 + ctx];    // MMA warp -> epilogue, per round: this round's dgrad (and everything issued before) completed
+    uint64_t* bar_tile = &bars[4 + ctx];    // MMA warp -> epilogue, per tile: the tile's last weight-gradient MMAs completed
 
-    if (ltid == 0) { mbar_init(bar, 1); mbar_init(bar_w, 1); mbar_fence_init(); }
+    if (tid < 2) { mbar_init(&bars[tid], 128); mbar_init(&bars[2 + tid], 1); mbar_init(&bars[4 + tid], 1); mbar_fence_init(); }
     if (tid < 32) tmem_alloc<512>(&tmem_base_s);
     {   // transposed weights in consumption order, one copy for both contexts
         const __half* w0 = weights;
         const __half* wh = weights + HID * in_dim;
         const __half* wout = wh + (size_t)n_hidden * HID * HID;
-        load_tile_transposed(base_gen, 0, wout, OUT_PAD, HID, tid, 256);
+        load_tile_transposed(base_gen, 0, wout, OUT_PAD, HID, tid, DUAL_THREADS);
         for (uint32_t j = 0; j < n_hidden; ++j)
-            load_tile_transposed(base_gen, (1 + j) * W_SLOT_BYTES, wh + (size_t)(n_hidden - 1 - j) * HID * HID, HID, HID, tid, 256);
-        if (want_dx) load_tile_transposed(base_gen, (1 + n_hidden) * W_SLOT_BYTES, w0, HID, in_dim, tid, 256);
+            load_tile_transposed(base_gen, (1 + j) * W_SLOT_BYTES, wh + (size_t)(n_hidden - 1 - j) * HID * HID, HID, HID, tid, DUAL_THREADS);
+        if (want_dx) load_tile_transposed(base_gen, (1 + n_hidden) * W_SLOT_BYTES, w0, HID, in_dim, tid, DUAL_THREADS);
     }
     // the X buffer's padding columns [in_dim, 64) are never written by the row copies: clear them once
-    zero_tile_cols(x_addr, TILE_M, in_dim >> 3, ltid, 128);
+    if (!is_mma) zero_tile_cols(x_addr, TILE_M, in_dim >> 3, ltid, 128);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_ctx = tmem_base_s + ctx * 256u;
-    const uint32_t t_lane = tmem_ctx + ((lwarp * 32u) << 16);
     auto acc_addr = [&](uint32_t l) { return tmem_ctx + 64u + 64u * (l >> 1) + ((16u * (l & 1u)) << 16); };
     auto g_addr = [&](uint32_t i) { return c_base + (i & 1u) * A_TILE_BYTES; };
-    uint32_t phase = 0, phase_w = 0;
-    bool first_tile = true;
 
     const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     const uint32_t nrounds = 1 + n_hidden + (want_dx ? 1u : 0u);
     const uint32_t tstride = gridDim.x * 2u;
     const uint32_t tile0 = blockIdx.x + ctx * gridDim.x;
+    bool first_tile = true;
 
-    // ring refill: one commit group per (tile, buffer), also when there is nothing to copy
-    auto issue_load = [&](uint32_t t, uint32_t j) {
-        if (t < ntiles) {
-            const size_t r0 = (size_t)t * TILE_M;
-            const uint32_t rv = (uint32_t)((size_t)B - r0 < TILE_M ? (size_t)B - r0 : TILE_M);
-            if (j < num_layers)
-                load_tile_rowmajor_async_nocommit(f_base + j * A_TILE_BYTES, forward_buffer + ((size_t)(num_layers - 1 - j) * B + r0) * HID,
-                                                  TILE_M, HID, ltid, 128, rv);
-            else if constexpr (!FIELD_COLOR)
-                load_tile_rowmajor_async_nocommit(x_addr, inputs + r0 * in_dim, TILE_M, in_dim, ltid, 128, rv);
-        }
-        cp_async_commit();
-    };
-    for (uint32_t j = 0; j < nbuf; ++j) issue_load(tile0, j);
-
-    // per-row scalars travel one tile ahead in registers (as in the single-context kernel)
-    float nx_y[3] = {0.f, 0.f, 0.f}, nx_g[3] = {0.f, 0.f, 0.f}, nx_dir[3] = {0.f, 0.f, 0.f}, nx_dsig = 0.f;
-    uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
-    uint32_t nx_pad = 0;
-    auto preload_rows = [&](uint32_t t) {
-        if constexpr (FIELD_COLOR) {
-            const size_t rw = (size_t)t * TILE_M + ltid;
-            if (t < ntiles && rw < (size_t)B) {
-                if (fa.grad_h) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) nx_g[c] = __half2float(__ldg(fa.grad_h + rw * 3 + c));
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        nx_y[c] = __ldg(fa.rgb + rw * 3 + c);
-                        nx_g[c] = __ldg(fa.d_rgb + rw * 3 + c);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) nx_dir[c] = __ldg(fa.dirs + rw * 3 + c);
-                if (fa.d_sigma) nx_dsig = __ldg(fa.d_sigma + rw);
-                nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
-                nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
-                if (fa.pad) nx_pad = __ldg(reinterpret_cast<const unsigned short*>(fa.pad) + rw);
-            }
-        }
-    };
-    preload_rows(tile0);
-    uint4 nx_dy[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    auto preload_dy = [&](uint32_t t) {
-        if constexpr (!FIELD_COLOR) {
-#pragma unroll
-            for (uint32_t k = 0; k < 2; ++k) {
-                const uint32_t g = ltid + k * 128u;
-                const size_t rw = (size_t)t * TILE_M + (g >> 1);
-                nx_dy[k] = (t < ntiles && rw < (size_t)B) ? __ldg(reinterpret_cast<const uint4*>(grad + rw * OUT_PAD) + (g & 1u))
-                                                           : make_uint4(0, 0, 0, 0);
-            }
-        }
-    };
-    preload_dy(tile0);
-
-    for (uint32_t tile = tile0; tile < ntiles; tile += tstride) {
-        const size_t row0 = (size_t)tile * TILE_M;
-        const size_t row = row0 + ltid;
-        const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
-        const bool row_ok = ltid < rows_valid;
-        const uint32_t next_tile = tile + tstride;
-        const float cur_dsig = nx_dsig;
-        const uint4 cur_h0 = nx_h0, cur_h1 = nx_h1;
-        // dL/dy -> G1; FIELD_COLOR: the first-layer input row [SH | geo | pad] -> X (its last reader, the previous tile's tail MMA, is done)
-        if constexpr (FIELD_COLOR) {
-            uint32_t q0 = 0, q1 = 0;
-            if (row_ok) {
-                float dh[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (fa.grad_h) { dh[c] = nx_g[c]; continue; }
-                    const float y = nx_y[c];
-                    const float g = __half2float(__float2half_rn(nx_g[c]));
-                    dh[c] = g * (y * (1.0f - y));
-                }
-                q0 = pack_h2(dh[0], dh[1]);
-                q1 = pack_h2(dh[2], 0.f);
-            }
-            write_shgeo_row_regs(x_addr, ltid, row_ok, nx_dir[0], nx_dir[1], nx_dir[2], cur_h0, cur_h1, nx_pad);
-            preload_rows(next_tile);
-            st_shared_v4(g1_addr + sw128_off(ltid, 0), make_uint4(q0, q1, 0, 0));
-#pragma unroll
-            for (uint32_t c = 1; c < 8; ++c) st_shared_v4(g1_addr + sw128_off(ltid, c), make_uint4(0, 0, 0, 0));
-        } else {
-#pragma unroll
-            for (uint32_t k = 0; k < 2; ++k) {
-                const uint32_t g = ltid + k * 128u;
-                st_shared_v4(g1_addr + sw128_off(g >> 1, g & 1u), nx_dy[k]);
-            }
-            preload_dy(next_tile);
-            zero_tile_cols(g1_addr, TILE_M, OUT_PAD >> 3, ltid, 128);
-        }
-
-        for (uint32_t r = 0; r < nrounds; ++r) {
-            const bool to_inputs = want_dx && (r == nrounds - 1);
-            const bool last_round = (r == nrounds - 1);
-            const uint32_t K = (r == 0) ? OUT_PAD : HID;
-            const uint32_t N = to_inputs ? in_dim : HID;
-            const uint32_t a_in = (r == 0) ? g1_addr : g_addr(r - 1);
-            // ring buffer r of THIS tile (H for this round's mask and weight gradient; X in the input-gradient round) has landed:
-            // groups committed after it = (num_layers - r) of this tile + (r - 1) refills for the next tile.  Waiting here lets ONE
-            // barrier publish both the previous epilogue's dPre tile and the copied tile.
-            cp_async_wait_pending(r == 0 ? num_layers : num_layers - 1);
-            fence_async_smem();
-            fence_before_sync();
-            bar_sync_128(bar_id);
-            if (lwarp == 0) {
-                if (ltid == 0) {
-                    fence_after_sync();
-                    // dgrad first and committed on its own: the epilogue below needs only this result ...
+    if (is_mma) {
+        // ------------------------------------------------------------------ MMA-issue warp of context `ctx`
+        uint32_t ph_ready = 0;
+        for (uint32_t tile = tile0; tile < ntiles; tile += tstride) {
+            for (uint32_t r = 0; r < nrounds; ++r) {
+                const bool to_inputs = want_dx && (r == nrounds - 1);
+                const uint32_t K = (r == 0) ? OUT_PAD : HID;
+                const uint32_t N = to_inputs ? in_dim : HID;
+                const uint32_t a_in = (r == 0) ? g1_addr : g_addr(r - 1);
+                mbar_wait(bar_ready, ph_ready);
+                ph_ready ^= 1u;
+                fence_after_sync();
+                if (lane == 0) {
+                    // dgrad first and committed on its own: the epilogue needs only this result ...
                     issue_layer(tmem_ctx, a_in, w_addr + r * W_SLOT_BYTES, N, K);
-                    mma_commit(bar);
-                    // ... while the weight gradient of the SAME matmul (P = this round's input gradient tile, Q = ring buffer r) runs
-                    // underneath it.  tcgen05.mma executes in issue order, so the next round's commit also covers these.
+                    mma_commit(bar_done);
+                    // ... while the weight gradient of the same matmul runs underneath it
                     if (r == 0) issue_wgrad(acc_addr(nmat - 1), g1_addr, f_base, first_tile ? 0u : 1u);
                     else issue_wgrad(acc_addr(num_layers - r), a_in, f_base + r * A_TILE_BYTES, first_tile ? 0u : 1u);
-                    if (last_round && want_dx) mma_commit(bar_w);
+                    if (to_inputs) mma_commit(bar_tile);
                 }
                 __syncwarp();
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            fence_after_sync();
-            if (!to_inputs) {
-                const uint32_t gw = g_addr(r), fw = f_base + r * A_TILE_BYTES;
+            if (!want_dx) {      // no input-gradient round: the weight gradient of matmul 0 (P = dPre_0, Q = X) is issued on its own
+                mbar_wait(bar_ready, ph_ready);
+                ph_ready ^= 1u;
+                fence_after_sync();
+                if (lane == 0) {
+                    issue_wgrad(acc_addr(0), g_addr(n_hidden), x_addr, first_tile ? 0u : 1u);
+                    mma_commit(bar_tile);
+                }
+                __syncwarp();
+            }
+            first_tile = false;
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warpgroup of context `ctx` (thread = batch row)
+        const uint32_t t_lane = tmem_ctx + ((lwarp * 32u) << 16);
+        uint32_t ph_done = 0, ph_tile = 0;
+        // ring refill: one commit group per (tile, buffer), also when there is nothing to copy
+        auto issue_load = [&](uint32_t t, uint32_t j) {
+            if (t < ntiles) {
+                const size_t r0 = (size_t)t * TILE_M;
+                const uint32_t rv = (uint32_t)((size_t)B - r0 < TILE_M ? (size_t)B - r0 : TILE_M);
+                if (j < num_layers)
+                    load_tile_rowmajor_async_nocommit(f_base + j * A_TILE_BYTES, forward_buffer + ((size_t)(num_layers - 1 - j) * B + r0) * HID,
+                                                      TILE_M, HID, ltid, 128, rv);
+                else if constexpr (!FIELD_COLOR)
+                    load_tile_rowmajor_async_nocommit(x_addr, inputs + r0 * in_dim, TILE_M, in_dim, ltid, 128, rv);
+            }
+            cp_async_commit();
+        };
+        for (uint32_t j = 0; j < nbuf; ++j) issue_load(tile0, j);
+
+        // per-row scalars travel one tile ahead in registers (as in the single-context kernel)
+        float nx_y[3] = {0.f, 0.f, 0.f}, nx_g[3] = {0.f, 0.f, 0.f}, nx_dir[3] = {0.f, 0.f, 0.f}, nx_dsig = 0.f;
+        uint4 nx_h0 = make_uint4(0, 0, 0, 0), nx_h1 = make_uint4(0, 0, 0, 0);
+        uint32_t nx_pad = 0;
+        auto preload_rows = [&](uint32_t t) {
+            if constexpr (FIELD_COLOR) {
+                const size_t rw = (size_t)t * TILE_M + ltid;
+                if (t < ntiles && rw < (size_t)B) {
+                    if (fa.grad_h) {
 #pragma unroll
-                for (uint32_t half_i = 0; half_i < 2; ++half_i) {
-                    uint32_t v[32];
-                    tmem_ld32(t_lane + half_i * 32, v);
-                    uint4 f[4];
+                        for (int c = 0; c < 3; ++c) nx_g[c] = __half2float(__ldg(fa.grad_h + rw * 3 + c));
+                    } else {
 #pragma unroll
-                    for (uint32_t c = 0; c < 4; ++c) f[c] = ld_shared_v4(fw + sw128_off(ltid, half_i * 4 + c));
-                    tmem_ld_wait();
-                    const __half2* fh = reinterpret_cast<const __half2*>(f);
-                    uint32_t p[16];
-#pragma unroll
-                    for (uint32_t i = 0; i < 16; ++i) {
-                        const float2 ff = __half22float2(fh[i]);
-                        p[i] = pack_h2(act_bwd<ACT>(__uint_as_float(v[2 * i]), ff.x), act_bwd<ACT>(__uint_as_float(v[2 * i + 1]), ff.y));
+                        for (int c = 0; c < 3; ++c) {
+                            nx_y[c] = __ldg(fa.rgb + rw * 3 + c);
+                            nx_g[c] = __ldg(fa.d_rgb + rw * 3 + c);
+                        }
                     }
 #pragma unroll
-                    for (uint32_t c = 0; c < 4; ++c)
-                        st_shared_v4(gw + sw128_off(ltid, half_i * 4 + c), make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]));
+                    for (int c = 0; c < 3; ++c) nx_dir[c] = __ldg(fa.dirs + rw * 3 + c);
+                    if (fa.d_sigma) nx_dsig = __ldg(fa.d_sigma + rw);
+                    nx_h0 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16));
+                    nx_h1 = __ldg(reinterpret_cast<const uint4*>(fa.h_sigma + rw * 16) + 1);
+                    if (fa.pad) nx_pad = __ldg(reinterpret_cast<const unsigned short*>(fa.pad) + rw);
                 }
-            } else if constexpr (FIELD_COLOR) {
-                uint32_t v[16];
-                tmem_ld16(t_lane + 16, v);
-                tmem_ld_wait();
+            }
+        };
+        preload_rows(tile0);
+        uint4 nx_dy[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        auto preload_dy = [&](uint32_t t) {
+            if constexpr (!FIELD_COLOR) {
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k) {
+                    const uint32_t g = ltid + k * 128u;
+                    const size_t rw = (size_t)t * TILE_M + (g >> 1);
+                    nx_dy[k] = (t < ntiles && rw < (size_t)B) ? __ldg(reinterpret_cast<const uint4*>(grad + rw * OUT_PAD) + (g & 1u))
+                                                               : make_uint4(0, 0, 0, 0);
+                }
+            }
+        };
+        preload_dy(tile0);
+        // this thread's row inside a swizzled tile: chunk c sits at row_off + ((c << 4) ^ row_xor)
+        const uint32_t row_off = ltid * 128u, row_xor = (ltid & 7u) << 4;
+
+        for (uint32_t tile = tile0; tile < ntiles; tile += tstride) {
+            const size_t row0 = (size_t)tile * TILE_M;
+            const size_t row = row0 + ltid;
+            const uint32_t rows_valid = (uint32_t)((size_t)B - row0 < TILE_M ? (size_t)B - row0 : TILE_M);
+            const bool row_ok = ltid < rows_valid;
+            const uint32_t next_tile = tile + tstride;
+            const float cur_dsig = nx_dsig;
+            const uint4 cur_h0 = nx_h0, cur_h1 = nx_h1;
+            // dL/dy -> G1; FIELD_COLOR: the first-layer input row [SH | geo | pad] -> X (all MMAs of the previous tile have completed)
+            if constexpr (FIELD_COLOR) {
+                uint32_t q0 = 0, q1 = 0;
                 if (row_ok) {
-                    const float h0 = __low2float(*reinterpret_cast<const __half2*>(&cur_h0.x));
-                    const float g0 = fa.d_sigma ? cur_dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) : 0.f;
-                    uint32_t p[8];
-                    p[0] = pack_h2(g0, __uint_as_float(v[0]));
+                    float dh[3];
 #pragma unroll
-                    for (uint32_t i = 1; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i - 1]), __uint_as_float(v[2 * i]));
-                    uint4* o = reinterpret_cast<uint4*>(fa.dys_out + row * 16);
-                    o[0] = make_uint4(p[0], p[1], p[2], p[3]);
-                    o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                    for (int c = 0; c < 3; ++c) {
+                        if (fa.grad_h) { dh[c] = nx_g[c]; continue; }
+                        const float y = nx_y[c];
+                        const float g = __half2float(__float2half_rn(nx_g[c]));
+                        dh[c] = g * (y * (1.0f - y));
+                    }
+                    q0 = pack_h2(dh[0], dh[1]);
+                    q1 = pack_h2(dh[2], 0.f);
                 }
-            } else {
-                __half* gi = grad_inputs + row * in_dim;
-                for (uint32_t c0 = 0; c0 < in_dim; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(t_lane + c0, v);
-                    tmem_ld_wait();
-                    uint32_t p[8];
+                write_shgeo_row_regs(x_addr, ltid, row_ok, nx_dir[0], nx_dir[1], nx_dir[2], cur_h0, cur_h1, nx_pad);
+                preload_rows(next_tile);
+                st_shared_v4(g1_addr + row_off + (0u ^ row_xor), make_uint4(q0, q1, 0, 0));
 #pragma unroll
-                    for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                for (uint32_t c = 1; c < 8; ++c) st_shared_v4(g1_addr + row_off + ((c << 4) ^ row_xor), make_uint4(0, 0, 0, 0));
+            } else {
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k) {
+                    const uint32_t g = ltid + k * 128u;
+                    st_shared_v4(g1_addr + sw128_off(g >> 1, g & 1u), nx_dy[k]);
+                }
+                preload_dy(next_tile);
+                zero_tile_cols(g1_addr, TILE_M, OUT_PAD >> 3, ltid, 128);
+            }
+
+            for (uint32_t r = 0; r < nrounds; ++r) {
+                const bool to_inputs = want_dx && (r == nrounds - 1);
+                // ring buffer r of THIS tile (H for this round's mask and weight gradient; X in the input-gradient round) has landed:
+                // groups committed after it = (num_layers - r) of this tile + (r - 1) refills for the next tile
+                cp_async_wait_pending(r == 0 ? num_layers : num_layers - 1);
+                fence_async_smem();            // my st.shared (dPre tile / G1 / X) and my landed copies -> visible to the tensor core
+                fence_before_sync();           // my tcgen05.ld of the previous round are ordered before the MMA warp's next issue
+                mbar_arrive(bar_ready);
+                mbar_wait(bar_done, ph_done);
+                ph_done ^= 1u;
+                fence_after_sync();
+                if (!to_inputs) {
+                    const uint32_t gw = g_addr(r) + row_off, fw = f_base + r * A_TILE_BYTES + row_off;
+#pragma unroll
+                    for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + half_i * 32, v);
+                        uint4 f[4];
+#pragma unroll
+                        for (uint32_t c = 0; c < 4; ++c) f[c] = ld_shared_v4(fw + (((half_i * 4 + c) << 4) ^ row_xor));
+                        tmem_ld_wait();
+                        uint32_t p[16];
+                        dpre_pack16<ACT>(v, f, p);
+#pragma unroll
+                        for (uint32_t c = 0; c < 4; ++c)
+                            st_shared_v4(gw + (((half_i * 4 + c) << 4) ^ row_xor), make_uint4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]));
+                    }
+                } else if constexpr (FIELD_COLOR) {
+                    uint32_t v[16];
+                    tmem_ld16(t_lane + 16, v);
+                    tmem_ld_wait();
                     if (row_ok) {
-                        uint4* o = reinterpret_cast<uint4*>(gi + c0);
+                        const float h0 = __low2float(*reinterpret_cast<const __half2*>(&cur_h0.x));
+                        const float g0 = fa.d_sigma ? cur_dsig * expf(fminf(fmaxf(h0, -15.f), 15.f)) : 0.f;
+                        uint32_t p[8];
+                        p[0] = pack_h2(g0, __uint_as_float(v[0]));
+#pragma unroll
+                        for (uint32_t i = 1; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i - 1]), __uint_as_float(v[2 * i]));
+                        uint4* o = reinterpret_cast<uint4*>(fa.dys_out + row * 16);
                         o[0] = make_uint4(p[0], p[1], p[2], p[3]);
                         o[1] = make_uint4(p[4], p[5], p[6], p[7]);
                     }
-                }
-            }
-            // ring buffer r-1: its last reader (the previous round's weight gradient) completed before this round's dgrad did;
-            // it takes the NEXT tile's activation tile.  Issued after the epilogue so the copies' issue slots are off the round's chain.
-            if (r >= 1) issue_load(next_tile, r - 1);
-        }
-
-        // tile tail: without an input-gradient round the weight gradient of matmul 0 (P = dPre_0, Q = X) still has to be issued
-        if (!want_dx) {
-            cp_async_wait_pending(num_layers - 1);          // X of this tile
-            fence_async_smem();
-            fence_before_sync();
-            bar_sync_128(bar_id);
-            if (lwarp == 0) {
-                if (ltid == 0) {
-                    fence_after_sync();
-                    issue_wgrad(acc_addr(0), g_addr(n_hidden), x_addr, first_tile ? 0u : 1u);
-                    mma_commit(bar_w);
-                }
-                __syncwarp();
-            }
-        }
-        // every MMA of this tile has completed (dPre tiles, X and the ring buffers still referenced are free again)
-        mbar_wait(bar_w, phase_w);
-        phase_w ^= 1u;
-        fence_after_sync();
-        for (uint32_t j = nrounds - 1; j < nbuf; ++j) issue_load(next_tile, j);
-        first_tile = false;
-    }
-    cp_async_wait_all();
-
-    // flush this context's weight-gradient accumulators (fp32) into the workspace laid out like `weights`
-    if (!first_tile) {
-        for (uint32_t lp = 0; lp < (nmat + 1) / 2; ++lp) {
-            const uint32_t l = lp * 2 + (lane >> 4);
-            const uint32_t m = lwarp * 16 + (lane & 15u);
-            uint32_t Mv, Nv, ws_off;
-            if (l == 0) { Mv = HID; Nv = in_dim; ws_off = 0; }
-            else if (l < nmat - 1) { Mv = HID; Nv = HID; ws_off = HID * in_dim + (l - 1) * HID * HID; }
-            else { Mv = OUT_PAD; Nv = HID; ws_off = HID * in_dim + (num_layers - 1) * HID * HID; }
+                } else {
+                    __half* gi = grad_inputs + row * in_dim;
+                    for (uint32_t c0 = 0; c0 < in_dim; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(t_lane + c0, v);
+                        tmem_ld_wait();
+                        uint32_t p[8];
 #pragma unroll
-            for (uint32_t half_i = 0; half_i < 2; ++half_i) {
-                uint32_t v[32];
-                tmem_ld32(t_lane + 64u + 64u * lp + half_i * 32, v);
-                tmem_ld_wait();
-                if (l < nmat && m < Mv) {
-                    float* dst = wgrad_ws + ws_off + (size_t)m * Nv;
+                        for (uint32_t i = 0; i < 8; ++i) p[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        if (row_ok) {
+                            uint4* o = reinterpret_cast<uint4*>(gi + c0);
+                            o[0] = make_uint4(p[0], p[1], p[2], p[3]);
+                            o[1] = make_uint4(p[4], p[5], p[6], p[7]);
+                        }
+                    }
+                }
+                // ring buffer r-1: its last reader (the previous round's weight gradient) completed before this round's dgrad did;
+                // it takes the NEXT tile's activation tile
+                if (r >= 1) issue_load(next_tile, r - 1);
+            }
+            if (!want_dx) {      // hand dPre_0 and X to the MMA warp for the weight gradient of matmul 0
+                cp_async_wait_pending(num_layers - 1);
+                fence_async_smem();
+                fence_before_sync();
+                mbar_arrive(bar_ready);
+            }
+            // every MMA of this tile has completed: dPre tiles, X and the ring buffers still referenced are free again
+            mbar_wait(bar_tile, ph_tile);
+            ph_tile ^= 1u;
+            fence_after_sync();
+            for (uint32_t j = nrounds - 1; j < nbuf; ++j) issue_load(next_tile, j);
+            first_tile = false;
+        }
+        cp_async_wait_all();
+
+        // flush this context's weight-gradient accumulators (fp32) into the workspace laid out like `weights`
+        if (!first_tile) {
+            for (uint32_t lp = 0; lp < (nmat + 1) / 2; ++lp) {
+                const uint32_t l = lp * 2 + (lane >> 4);
+                const uint32_t m = lwarp * 16 + (lane & 15u);
+                uint32_t Mv, Nv, ws_off;
+                if (l == 0) { Mv = HID; Nv = in_dim; ws_off = 0; }
+                else if (l < nmat - 1) { Mv = HID; Nv = HID; ws_off = HID * in_dim + (l - 1) * HID * HID; }
+                else { Mv = OUT_PAD; Nv = HID; ws_off = HID * in_dim + (num_layers - 1) * HID * HID; }
 #pragma unroll
-                    for (uint32_t i = 0; i < 32; ++i) {
-                        const uint32_t n = half_i * 32 + i;
-                        if (n < Nv) atomicAdd(dst + n, __uint_as_float(v[i]));
+                for (uint32_t half_i = 0; half_i < 2; ++half_i) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + 64u + 64u * lp + half_i * 32, v);
+                    tmem_ld_wait();
+                    if (l < nmat && m < Mv) {
+                        float* dst = wgrad_ws + ws_off + (size_t)m * Nv;
+#pragma unroll
+                        for (uint32_t i = 0; i < 32; ++i) {
+                            const uint32_t n = half_i * 32 + i;
+                            if (n < Nv) atomicAdd(dst + n, __uint_as_float(v[i]));
+                        }
                     }
                 }
             }
@@ -1421,7 +1454,7 @@ extern "C" int ngp_ffmlp_backward_ex(const void* grad, const void* inputs, const
         NGP_DISPATCH_ACT(activation,
             rc = set_smem(k_ffmlp_backward_dual<A, false>, smem_dual, "ffmlp_backward");
             if (rc == NGP_OK)
-                k_ffmlp_backward_dual<A, false><<<grid, 256, smem_dual, st>>>((const __half*)grad, (const __half*)inputs, (const __half*)weights,
+                k_ffmlp_backward_dual<A, false><<<grid, DUAL_THREADS, smem_dual, st>>>((const __half*)grad, (const __half*)inputs, (const __half*)weights,
                                                                               (const __half*)forward_buffer, gi, (float*)workspace, B, input_dim,
                                                                               num_layers, FieldArgs{}))
         if (rc) return rc;
@@ -1640,7 +1673,7 @@ extern "C" int ngp_field_color_backward_ex(const float* d_rgb, const float* rgb,
             rc = set_smem(k_ffmlp_backward_dual<ACT_RELU, true>, smem_dual, "field_color_backward");
             if (rc) return rc;
             // grad_inputs is only a non-null flag here (the epilogue writes dys_out instead)
-            k_ffmlp_backward_dual<ACT_RELU, true><<<grid, 256, smem_dual, st>>>(nullptr, nullptr, (const __half*)weights, (const __half*)forward_buffer,
+            k_ffmlp_backward_dual<ACT_RELU, true><<<grid, DUAL_THREADS, smem_dual, st>>>(nullptr, nullptr, (const __half*)weights, (const __half*)forward_buffer,
                                                                                 (__half*)dys_out, (float*)workspace, M, 32, num_layers, fa);
         } else {
             const uint32_t nslots = 1 + (num_layers - 1) + 1;

@@ -16,6 +16,7 @@
 //     with red.global.add.noftz.f16x2 / red.global.add.v2.f32 (no return value, one op per corner),
 //   * everything runs on the caller's stream.
 #include "common.cuh"
+#include <stdlib.h>
 #include "grid.cuh"
 
 namespace ngp {
@@ -500,6 +501,24 @@ __global__ void k_level_scales(float* out, uint32_t L, float S, uint32_t H) {
     if (l < L) out[l] = level_scale(l, S, H);
 }
 
+// ---- L2 reduction-rate probe (measurement hook, not part of the reference ABI) -----------------------------------------------
+// What bounds k_grid_backward is not HBM: the fp16 gradient table (24.5 MB) lives in L2 and every corner update is an L2 reduction
+// op.  This kernel measures the device's sustained rate for exactly that access pattern — `ops_per_thread` reductions per thread at
+// pseudo-random, suitably aligned entries of a table of `entries` f16x2 values — for the three op widths the scatter uses
+// (mode 0: 4-byte f16x2, 1: 8-byte v2.f16x2, 2: 16-byte v4.f16x2).  bench.py reports the scatter against this measured ceiling.
+__global__ void k_red_probe(__half* __restrict__ table, uint32_t entries, uint32_t ops_per_thread, int mode) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    const __half2 one = __floats2half2_rn(1.0f, 1.0f);
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(&one);
+    for (uint32_t i = 0; i < ops_per_thread; ++i) {
+        x = x * 1664525u + 1013904223u;                       // LCG: a different random entry per op and per lane
+        const uint32_t e = (x >> 8) % entries;
+        if (mode == 0) red_add_h2(table + (size_t)e * 2, one);
+        else if (mode == 1) red_add_h4(table + (size_t)(e & ~1u) * 2, one, one);
+        else red_add_h8(table + (size_t)(e & ~3u) * 2, u, u, u, u);
+    }
+}
+
 // ---- dispatch -------------------------------------------------------------------------------
 template <typename T, uint32_t D, uint32_t C>
 static int launch_fwd(const float* inputs, const void* emb, const int* offsets, void* out, uint32_t B,
@@ -525,8 +544,11 @@ static int launch_bwd(const void* grad, const float* inputs, const int* offsets,
     const uint32_t nw = L < 16 ? L : 16;
     dim3 block(32, nw);
     dim3 grid(div_up(B, TILE_PTS));
-    // 16-byte vector reductions need a 16-byte aligned table (level offsets are multiples of 8 entries: grid.py:124)
-    const bool quad_ok = (reinterpret_cast<uintptr_t>(gemb) & 15u) == 0;
+    // 16-byte quad reductions (x / x+1 in one aligned quad of entries -> one REDG.F16x8) are implemented but OFF: measured on the bench
+    // scene they make the kernel slower (1.73 -> 1.80 ms; ncu r2: the scatter is issue-bound at 74 % issue-slot utilisation and the
+    // quad selection adds ~100 instructions per warp-level, more than the ~12 % fewer reduction ops save).  NGP_GRID_QUAD_RED=1 enables.
+    static const bool quad_env = [] { const char* e = getenv("NGP_GRID_QUAD_RED"); return e && e[0] == '1'; }();
+    const bool quad_ok = quad_env && (reinterpret_cast<uintptr_t>(gemb) & 15u) == 0;
     k_grid_backward<T, D, C><<<grid, block, 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
                                                      gridtype, ac, interp, level_major, quad_ok);
     int rc = check_launch("grid_encode_backward");
@@ -608,6 +630,14 @@ extern "C" int ngp_grad_total_variation(const void* inputs, const void* embeddin
     if (dtype == NGP_F16) { NGP_DISPATCH_DC(launch_tv, __half, inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, align_corners != 0, st) }
     if (dtype == NGP_F32) { NGP_DISPATCH_DC(launch_tv, float, inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, align_corners != 0, st) }
     return fail(NGP_EINVAL, "grad_total_variation: dtype must be NGP_F32 or NGP_F16");
+}
+
+// measurement hook: `blocks` x 256 threads x ops_per_thread reductions into table[entries] (f16x2 entries; entries % 4 == 0)
+extern "C" int ngp_debug_red_probe(void* table_f16x2, uint32_t entries, uint32_t blocks, uint32_t ops_per_thread, int mode,
+                                   ngp_stream_t stream) {
+    if (!table_f16x2 || entries < 4 || (entries & 3u) || mode < 0 || mode > 2) return fail(NGP_EINVAL, "debug_red_probe: bad arguments");
+    k_red_probe<<<blocks, 256, 0, as_stream(stream)>>>((__half*)table_f16x2, entries, ops_per_thread, mode);
+    return check_launch("debug_red_probe");
 }
 
 // test hook (not part of the reference ABI): device-computed per-level scales
