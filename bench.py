@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-prefetch", action="store_true", help="march each step's rays inside that step instead of one step ahead on a low-priority stream")
     ap.add_argument("--prefetch-point", default="auto", choices=["auto", "start", "exchange"])
     ap.add_argument("--mlp-backward", default="dual", choices=["dual", "single"], help="two-context MLP backward kernel (default) or the single-context one")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"], help="gradient exchange at N > 1: fused peer-memory reduce-scatter + sharded Adam + operand all-gather (csrc/exchange.cu; auto = use it when the ranks can map each other's memory) or NCCL all-reduce + full optimizer pass per rank")
     ap.add_argument("--long-steps", type=int, default=200, help="extra, longer timed region reported as `long_run` (0 = skip)")
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c5", "infer"], help="BASELINE.json config: c2 = training step (default; c4 = the same under torchrun), c1 = GridEncoder fwd/bwd 64k points, c3 = fused density inference 4096x1024, c5 = SDF 1M points, infer = full-frame eval render")
     return ap.parse_args()
@@ -288,7 +289,9 @@ def main():
     fstep = None
     if use_fused_opt:
         from ngp_optim import FusedFieldOptimizer
-        fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0)
+        fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0,
+                                   exchange=args.exchange)
+        log(f"gradient exchange: {'peer memory (fused with the optimizer)' if fopt.px is not None else ('nccl all-reduce' if world > 1 else 'none (1 GPU)')}")
 
         from nerf_step import FusedTrainStep
         ppoint = args.prefetch_point if args.prefetch_point != "auto" else ("exchange" if world > 1 else "start")
@@ -597,10 +600,17 @@ def main():
             "kernel_time_share": kern_ms / ms_eager, "kernels": breakdown,
             "cuda_graph": graphs is not None, "ms_per_step_eager_unpipelined": ms_eager / args.steps,
             "mlp_backward_kernel": args.mlp_backward,
+            "exchange": (("peer-memory reduce-scatter + sharded Adam + fp16 operand all-gather in 3 kernels + 3 flag barriers (csrc/exchange.cu)"
+                          if (use_fused_opt and fopt.px is not None) else "nccl all-reduce of the fp16 sink + full optimizer pass per rank") if world > 1 else "none"),
             "pipelining": {"field_chunks": args.chunks if use_fused_opt else 1, "march_prefetch": bool(prefetch),
                            "prefetch_point": (fstep.prefetch_point if fstep is not None else None),
                            "note": "per-kernel figures (`kernels`, `roofline`) come from an eager pass with the pipelining switched off, so that each launch is timed alone; the headline is the pipelined, graph-replayed step"},
             "long_run": long_run, "timed_region_s": ms_total * 1e-3}
+
+    if use_fused_opt and fopt.px is not None:
+        line["exchange_error"] = fopt.px.error()        # non-zero = a flag barrier timed out (the numbers above are then void)
+        if line["exchange_error"]:
+            log(f"PEER EXCHANGE ERROR {line['exchange_error']}")
 
     # ---- the table scatter is an L2-reduction kernel (the fp16 gradient table is L2-resident: dram traffic is 0.18x the algorithmic
     # bytes): report it against the device's MEASURED reduction rate for the same access pattern as well (random f16x2 / v2.f16x2

@@ -149,6 +149,18 @@ int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float
                                       const int32_t* rays, const float* weights_sum,
                                       const float* image, uint32_t M, uint32_t N, float T_thresh,
                                       float* grad_sigmas, float* grad_rgbs, ngp_stream_t stream);
+/* Step-driver extensions (no reference counterpart).  _forward_mse = compositor + the training loss head in one launch: also forms
+ * pred = image + (1 - weights_sum) * bg against target [N,3] (indexed like image), the squared error per row of `rays` (sqerr [N]) and
+ * g_image [N,3] / g_ws [N] = d(loss * *scale)/d(image, weights_sum) for loss = inv_norm / 2 * sum(sqerr) (inv_norm = 2 / (3 R) for the mean
+ * of nerf/utils.py:866); replaces the elementwise / reduction launches between ngp_composite_rays_train_forward and _backward.
+ * step_counter_push: step_counter[ring] = counter; ring = (ring + 1) % 16; ++nsteps (renderer.py:281-283, on the device). */
+int ngp_composite_rays_train_forward_mse(const float* sigmas, const float* rgbs, const float* deltas,
+                                         const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                         const float* target, float bg, float inv_norm, const float* scale,
+                                         float* weights_sum, float* depth, float* image, float* g_image,
+                                         float* g_ws, float* sqerr, ngp_stream_t stream);
+int ngp_step_counter_push(int32_t* ring, const int32_t* counter, int32_t* nsteps, int32_t* step_counter,
+                          ngp_stream_t stream);
 int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive,
                    const float* rays_t, const float* rays_o, const float* rays_d, float bound,
                    float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid,
@@ -229,6 +241,37 @@ int ngp_optim_adam_step(float* params, float* exp_avg, float* exp_avg_sq, void* 
                         uint64_t n, float lr, float beta1, float beta2, float eps, const void* state, int zero_grad,
                         ngp_stream_t stream);
 int ngp_optim_scaler_update(void* state, float growth, float backoff, int growth_interval, ngp_stream_t stream);
+/* ---- gradient exchange over NVLink peer memory, fused with the optimizer (the step's single exchange; the
+ * baseline it replaces is an NCCL all-reduce of the fp16 gradient bucket followed by ngp_optim_* over all parameters on every rank).
+ * One process per GPU; every rank allocates one peer-visible block with ngp_peer_alloc, ships the 64-byte CUDA IPC handle to the other
+ * ranks of the node and maps theirs with ngp_peer_open.  `*_host` arguments are HOST arrays of `world` device pointers (entry r = rank
+ * r's buffer as mapped in this process).  The flat parameter space is split into `world` shards (multiples of 8 elements):
+ *   ngp_exchange_barrier(slot 0)                      all local gradient buckets are complete
+ *   ngp_exchange_reduce(lo, count = my shard)         my bucket[shard] = fp16(sum over ranks, fp32 accumulate); inf/nan -> state.found_inf
+ *   ngp_exchange_barrier(slot 1, &found_inf, &found_inf)   everybody has read my bucket; found_inf OR-ed over ranks (GradScaler skip rule)
+ *   ngp_exchange_adam(...) per parameter piece        Adam on my shard's fp32 masters / moments; the updated fp16 operand copy is
+ *                                                     stored into EVERY rank's shadow (the all-gather half of the exchange)
+ *   ngp_exchange_zero                                 clear my whole bucket for the next step
+ *   ngp_exchange_barrier(slot 2)                      all shadows complete
+ *   ngp_optim_scaler_update
+ * Barriers are one-warp kernels on monotonic device-resident epochs (graph-replay safe); a peer that does not arrive within
+ * timeout_ms (0 = 2000) raises the pad's error word (ngp_exchange_error) instead of hanging the device. ---- */
+int    ngp_peer_alloc(size_t bytes, void** ptr_out, void* handle_out_host /* 64 bytes */);
+int    ngp_peer_open(const void* handle_host /* 64 bytes */, void** ptr_out);
+int    ngp_peer_close(void* ptr);
+int    ngp_peer_free(void* ptr);
+size_t ngp_exchange_pad_bytes(void);           /* size of a signal pad (zero-initialised peer memory) */
+int    ngp_exchange_error(const void* my_pad, uint32_t* error_out_host);
+int    ngp_exchange_barrier(void* const* pads_host, uint32_t rank, uint32_t world, uint32_t slot, const int32_t* flag_in,
+                            int32_t* flag_out, uint32_t timeout_ms, ngp_stream_t stream);
+int    ngp_exchange_reduce(void* const* sinks_host, uint32_t rank, uint32_t world, uint64_t lo, uint64_t count, void* state,
+                           ngp_stream_t stream);
+/* params = fp32 master of ONE parameter tensor whose element 0 has flat index seg_off; exp_avg / exp_avg_sq are the flat moment
+ * arrays; [lo, lo + count) = the piece of this rank's shard that lies inside that tensor. */
+int    ngp_exchange_adam(float* params, float* exp_avg_flat, float* exp_avg_sq_flat, void* my_sink, void* const* shadows_host,
+                         uint32_t world, uint64_t seg_off, uint64_t lo, uint64_t count, float lr, float beta1, float beta2,
+                         float eps, const void* state, ngp_stream_t stream);
+int    ngp_exchange_zero(void* my_sink, uint64_t n, ngp_stream_t stream);
 /* ---- occupancy-grid maintenance (replaces the Python/torch op sequences of
  * nerf/renderer.py:380-442 mark_untrained_grid and :445-538 update_extra_state).  density_grid is float [C, H^3] in Morton
  * order, bitfield uint8 [C*H^3/8] (the marcher's format, raymarching.cu:279-288).  All random numbers are caller-provided

@@ -113,3 +113,28 @@ def test_occupancy_sync_and_seed_lock():
     assert torch.equal(l0, l1)                          # locked draws identical on both ranks
     assert not torch.equal(a0, a1)                      # per-rank streams restored
 
+
+
+def test_exchange_shards_partition_the_flat_parameter_space():
+    """Host logic of the fused exchange (ngp_dp.shard_bounds / segment_pieces): shards tile [0, n) on multiples of 8 and their
+    pieces tile every parameter segment exactly once."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "torch-ngp_b200")]
+    import ngp_dp
+    segs = [(0, 12239728), (12239728, 7168), (12246896, 11264)]
+    n = 12258160
+    for world in (1, 2, 3, 4, 7, 8, 16):
+        b = ngp_dp.shard_bounds(n, world)
+        assert b[0] == 0 and b[-1] == n and len(b) == world + 1
+        assert all(x % 8 == 0 for x in b) and all(b[i] <= b[i + 1] for i in range(world))
+        sizes = [b[i + 1] - b[i] for i in range(world)]
+        assert max(sizes) - min(sizes) <= 8
+        covered = [0] * len(segs)
+        for r in range(world):
+            for i, a, cnt in ngp_dp.segment_pieces(segs, b[r], b[r + 1]):
+                off, k = segs[i]
+                assert off <= a and a + cnt <= off + k and a % 8 == 0 and cnt % 8 == 0
+                covered[i] += cnt
+        assert covered == [k for _, k in segs]
+    import pytest
+    with pytest.raises(ValueError):
+        ngp_dp.shard_bounds(1001, 2)

@@ -34,3 +34,30 @@ def test_two_rank_reduced_sink_equals_single_gpu_sink(tmp_path):
     # entries no ray touched stay exactly zero on both sides
     assert bool(((a == 0) == (b == 0)).float().mean() > 0.999)
     print(f"2-rank reduced sink vs 1-GPU sink: cos={cos:.6f} max err {err:.2e} of max |g|")
+
+
+def _run_exchange_worker(mode, out, port):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "dp_exchange_worker.py"), out, mode],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert p.returncode == 0, (p.stdout[-1500:], p.stderr[-3000:])
+    return torch.load(out)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
+def test_peer_exchange_matches_nccl(tmp_path):
+    """The fused peer-memory exchange + sharded optimizer (csrc/exchange.cu) against NCCL all-reduce + the full optimizer pass on the same
+    gradients: 3 steps, the second one non-finite on one rank (skipped everywhere, loss scale halved)."""
+    peer = _run_exchange_worker("peer", str(tmp_path / "peer.pt"), 29543)
+    nccl = _run_exchange_worker("nccl", str(tmp_path / "nccl.pt"), 29545)
+    assert peer["scale"] == nccl["scale"] == 512.0                 # one backoff
+    assert int(peer["state"][3]) == int(nccl["state"][3]) == 2      # two steps actually taken
+    assert torch.equal(peer["shadow0"], peer["shadow1"])            # the skipped step changed nothing
+    for k in ("params", "exp_avg", "exp_avg_sq"):
+        a, b = peer[k].double(), nccl[k].double()
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err < 1e-6, (k, err)     # two summands: fp32-accumulated and fp16 sums round identically; Adam arithmetic is the same code
+    same = float((peer["shadow"] == nccl["shadow"]).float().mean())
+    assert same > 0.99999, same
+    print(f"peer vs nccl exchange: identical fp16 operand entries {same:.6f}")

@@ -187,6 +187,53 @@ def test_composite_train_vs_oracle_and_gradcheck():
     assert gs1.abs().sum().item() > 0
 
 
+def test_composite_forward_mse_head_and_counter_push():
+    """Step-driver extensions: the compositor with the fused loss head (ngp_composite_rays_train_forward_mse) against the plain compositor
+    followed by the torch expressions it replaces, and the device-side sample-count ring (ngp_step_counter_push)."""
+    from oracle import oracle as O
+    import raymarching
+    import _ngp_b200 as nb
+    N = 2048
+    rays_o, rays_d, bitfield, grid, noises = _scene(N)
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = O.near_far_from_aabb(rays_o.numpy(), rays_d.numpy(), aabb, 0.2)
+    M = N * 64                                  # some rays overflow the budget and composite to the background
+    ox, od_, odl, orays, ocnt = O.march_rays_train(rays_o.numpy(), rays_d.numpy(), bitfield.numpy(), 1.0, 0.0, 1024, 1, 128,
+                                                   M, nears, fars, noises.numpy())
+    m = min(int(ocnt[0]), M)
+    sig = torch.zeros(M); sig[:m] = torch.rand(m, generator=gen(20)) * 30
+    rgb = torch.zeros(M, 3); rgb[:m] = torch.rand(m, 3, generator=gen(21))
+    dl = torch.zeros(M, 2); dl[:m] = torch.from_numpy(odl[:m].copy())
+    sig, rgb, dl, rays_t = sig.cuda(), rgb.cuda(), dl.cuda(), torch.from_numpy(orays).cuda()
+    target = torch.rand(N, 3, generator=gen(24)).cuda()
+    ws, depth, image = raymarching.composite_rays_train(sig, rgb, dl, rays_t, 1e-4)
+    bg, R, scale = 1.0, float(4 * N), torch.tensor([128.0], device="cuda")
+    pred = image + (1 - ws).unsqueeze(-1) * bg
+    diff = pred - target
+    g_pred = diff * ((2.0 / (3.0 * R)) * scale)
+    g_ws = -(g_pred.sum(-1)) * bg
+    loss = (diff * diff).sum() / (3.0 * R)
+    f = dict(dtype=torch.float32, device="cuda")
+    ws2, dp2, im2 = torch.empty(N, **f), torch.empty(N, **f), torch.empty(N, 3, **f)
+    gi, gw, sq = torch.empty(N, 3, **f), torch.empty(N, **f), torch.empty(N, **f)
+    nb.call("ngp_composite_rays_train_forward_mse", sig.data_ptr(), rgb.data_ptr(), dl.data_ptr(), rays_t.data_ptr(), M, N, 1e-4,
+            target.data_ptr(), bg, float(2.0 / (3.0 * R)), scale.data_ptr(), ws2.data_ptr(), dp2.data_ptr(), im2.data_ptr(), gi.data_ptr(),
+            gw.data_ptr(), sq.data_ptr())
+    assert torch.equal(ws2, ws) and torch.equal(dp2, depth) and torch.equal(im2, image)      # same compositor arithmetic
+    assert rel_err(gi.cpu().numpy(), g_pred.cpu().numpy()) < 1e-6
+    assert rel_err(gw.cpu().numpy(), g_ws.cpu().numpy()) < 1e-6
+    assert abs(float(sq.sum() / (3.0 * R)) - float(loss)) < 1e-6 * float(loss)
+    # the ring: three pushes land in rows 0, 1, 2; row 15 wraps to 0
+    ring = torch.zeros(1, dtype=torch.int32, device="cuda"); nsteps = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sc = torch.zeros(16, 2, dtype=torch.int32, device="cuda")
+    for k in range(18):
+        counter = torch.tensor([100 + k, 7 + k], dtype=torch.int32, device="cuda")
+        nb.call("ngp_step_counter_push", ring.data_ptr(), counter.data_ptr(), nsteps.data_ptr(), sc.data_ptr())
+    torch.cuda.synchronize()
+    assert int(nsteps) == 18 and int(ring) == 2
+    assert sc[0].tolist() == [116, 23] and sc[1].tolist() == [117, 24] and sc[2].tolist() == [102, 9] and sc[15].tolist() == [115, 22]
+
+
 def test_inference_march_and_composite_vs_oracle():
     from oracle import oracle as O
     import raymarching

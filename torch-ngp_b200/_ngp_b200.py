@@ -46,6 +46,12 @@ _SIGNATURES = {
     "ngp_optim_check_finite": [_vp, _i32, _c.c_uint64, _vp, _vp],
     "ngp_optim_adam_step": [_vp, _vp, _vp, _vp, _i32, _vp, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _i32, _vp],
     "ngp_optim_scaler_update": [_vp, _f32, _f32, _i32, _vp],
+    "ngp_exchange_barrier": [_vp, _u32, _u32, _u32, _vp, _vp, _u32, _vp],
+    "ngp_exchange_reduce": [_vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _vp],
+    "ngp_exchange_adam": [_vp, _vp, _vp, _vp, _vp, _u32, _c.c_uint64, _c.c_uint64, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp],
+    "ngp_exchange_zero": [_vp, _c.c_uint64, _vp],
+    "ngp_composite_rays_train_forward_mse": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "ngp_step_counter_push": [_vp, _vp, _vp, _vp, _vp],
     "ngp_density_grid_mark_untrained": [_vp, _u32, _f32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _vp, _vp, _vp],
     "ngp_density_grid_occupied": [_vp, _u32, _u32, _vp, _vp, _vp, _vp],
     "ngp_density_grid_sample_full": [_u32, _u32, _f32, _vp, _vp, _vp],
@@ -69,7 +75,9 @@ _SIGNATURES = {
 # every symbol include/ngp_b200.h declares (tests check the .so exports all of them)
 EXPORTED = sorted(list(_SIGNATURES) + ["ngp_debug_set_mlp_backward", "ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
                                        "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes",
-                                       "ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"])
+                                       "ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes",
+                                       "ngp_peer_alloc", "ngp_peer_open", "ngp_peer_close", "ngp_peer_free", "ngp_exchange_pad_bytes",
+                                       "ngp_exchange_error"])
 
 _lib = None
 
@@ -100,6 +108,16 @@ def load():
     for name in ("ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"):
         getattr(lib, name).argtypes = [_u32, _u32]
         getattr(lib, name).restype = _sz
+    # peer-visible memory (CUDA IPC) and the exchange's host-side helpers: no stream argument
+    lib.ngp_peer_alloc.argtypes = [_sz, _c.POINTER(_vp), _vp]
+    lib.ngp_peer_open.argtypes = [_vp, _c.POINTER(_vp)]
+    lib.ngp_peer_close.argtypes = [_vp]
+    lib.ngp_peer_free.argtypes = [_vp]
+    lib.ngp_exchange_pad_bytes.argtypes = []
+    lib.ngp_exchange_pad_bytes.restype = _sz
+    lib.ngp_exchange_error.argtypes = [_vp, _c.POINTER(_u32)]
+    for name in ("ngp_peer_alloc", "ngp_peer_open", "ngp_peer_close", "ngp_peer_free", "ngp_exchange_error"):
+        getattr(lib, name).restype = _c.c_int
     _lib = lib
     return lib
 

@@ -226,181 +226,288 @@ __device__ __forceinline__ void red_add_f1(float* addr, float a) {
 // equal entry index (shuffle scan, fp32) and only the last lane of a run issues the reduction op:
 // the number of L2 atomics on the coarse levels drops by the run length, and the addends are summed
 // in fp32 before the single fp16 rounding (more accurate than one fp16 atomic per sample).
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// everything about a level that does not depend on the point: computed once per warp when the warp keeps its level for the whole
+// kernel (L <= warps per CTA — the persistent CTA then never repeats the exp2 / ceil / addressing-mode decision per tile)
+struct BwdLevel {
+    uint32_t off, size, res, mode;      // mode 0: dense strides, 1: xor-prime hash with a power-of-two table, 2: reference loop
+    float scale;
+};
+template <uint32_t D>
+__device__ __forceinline__ BwdLevel make_bwd_level(const int* __restrict__ offsets, uint32_t level, float S, uint32_t H,
+                                                   uint32_t gridtype, bool align_corners) {
+    BwdLevel P;
+    P.off = (uint32_t)__ldg(offsets + level);
+    P.size = (uint32_t)__ldg(offsets + level + 1) - P.off;
+    P.scale = level_scale(level, S, H);
+    P.res = (uint32_t)ceilf(P.scale) + 1;
+    const uint32_t r1 = align_corners ? P.res : P.res + 1;
+    unsigned long long cells = 1;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) cells = cells * r1 > 0xffffffffull ? 0x100000000ull : cells * r1;
+    P.mode = cells <= P.size ? 0u : ((gridtype == 0 && (P.size & (P.size - 1)) == 0) ? 1u : 2u);
+    return P;
+}
+// corner_indices() with the addressing mode already decided (same results)
+template <uint32_t D>
+__device__ __forceinline__ void corner_indices_mode(const BwdLevel& P, uint32_t gridtype, bool align_corners, const uint32_t pg[D],
+                                                    uint32_t out[1u << D]) {
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    if (P.mode == 0u) {
+        const uint32_t r1 = align_corners ? P.res : P.res + 1;
+        uint32_t stride[D], base = 0, st = 1;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) { stride[d] = st; base += pg[d] * st; st *= r1; }
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t v = base;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) if (idx & (1u << d)) v += stride[d];
+            out[idx] = v;
+        }
+    } else if (P.mode == 1u) {
+        uint32_t h0[D], h1[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) { h0[d] = pg[d] * primes[d]; h1[d] = h0[d] + primes[d]; }
+        const uint32_t mask = P.size - 1;
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t v = 0;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) v ^= (idx & (1u << d)) ? h1[d] : h0[d];
+            out[idx] = v & mask;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+            uint32_t pl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) pl[d] = pg[d] + ((idx >> d) & 1u);
+            out[idx] = level_index<D>(gridtype, align_corners, P.size, P.res, pl);
+        }
+    }
+}
+
+// Persistent CTAs (grid = min(tiles, 3 x SMs)) walk the 32-point tiles round-robin.  With `staged` the tile's inputs — the dL/dy rows
+// [32, L*C] and the coordinates [32, D] — are copied global -> shared with cp.async ONE TILE AHEAD (double buffer), fully coalesced,
+// and the 16 level-warps read them from shared memory (odd row pitch: conflict-free).  The unstaged form (level-major gradients,
+// entries that are not whole 32-bit words) loads them per warp from global: every warp re-reads the same 32 coordinate triples and
+// touches 32 sectors for its 32 x 4-byte gradient entries (ncu r2 of that form: L1/LSU 69 % busy, 29 % of the stall samples on the
+// CTA's first loads, issue slots 74 % busy with ~580 instructions per warp-level, ~150 of them per-level setup that is now hoisted).
 template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, (D <= 3 && C <= 2) ? 3 : 1)     // NeRF / SDF shapes: 40 registers, 3 CTAs per SM
 k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 const int* __restrict__ offsets, T* __restrict__ grad_table, const uint32_t B,
                 const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
-                const bool align_corners, const uint32_t interp, const bool level_major, const bool quad_ok) {
+                const bool align_corners, const uint32_t interp, const bool level_major, const bool staged) {
+    extern __shared__ __align__(16) uint32_t stage_sm[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x;
     const uint32_t warp = threadIdx.y;
     const uint32_t nwarp = blockDim.y;
-    const uint32_t b = blockIdx.x * TILE_PTS + lane;
+    const uint32_t tid = warp * 32 + lane, nthr = nwarp * 32;
     const uint32_t F = L * C;
-    bool active = b < B;
+    const uint32_t ntiles = div_up(B, TILE_PTS);
+    constexpr uint32_t EW = (C * (uint32_t)sizeof(T)) / 4;            // 32-bit words per (level, point) gradient entry (staged form)
+    const uint32_t row_words = (F * (uint32_t)sizeof(T)) / 4;
+    const uint32_t pitch = row_words | 1u;
+    const uint32_t buf_words = TILE_PTS * pitch + TILE_PTS * D;
+    auto issue = [&](uint32_t tile, uint32_t buf) {
+        if (tile < ntiles) {
+            uint32_t* sg = stage_sm + buf * buf_words;
+            float* sx = reinterpret_cast<float*>(sg + TILE_PTS * pitch);
+            const uint32_t b0 = tile * TILE_PTS;
+            const uint32_t npts = min(TILE_PTS, B - b0);
+            const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(grad + (size_t)b0 * F);
+            for (uint32_t i = tid; i < npts * row_words; i += nthr) {
+                const uint32_t r = i / row_words, w = i - r * row_words;
+                cp_async_4(sg + r * pitch + w, gsrc + i);
+            }
+            const float* xsrc = inputs + (size_t)b0 * D;
+            for (uint32_t i = tid; i < npts * D; i += nthr) cp_async_4(sx + i, xsrc + i);
+        }
+        cp_async_commit_group();          // one group per call, also when empty: the wait distance below stays fixed
+    };
+    if (staged) issue(blockIdx.x, 0);
+    const bool fixed_level = L <= nwarp;
+    const BwdLevel P_fixed = make_bwd_level<D>(offsets, warp < L ? warp : 0u, S, H, gridtype, align_corners);
 
-    float x[D];
-#pragma unroll
-    for (uint32_t d = 0; d < D; ++d) {
-        x[d] = active ? __ldg(inputs + (size_t)b * D + d) : 0.5f;
-        if (x[d] < 0 || x[d] > 1) active = false;   // grad_table starts at zero (gridencoder.cu:284-289)
-    }
-    if (__ballot_sync(FULL, active) == 0) return;    // warp-uniform exit
-    if (!active) {
-#pragma unroll
-        for (uint32_t d = 0; d < D; ++d) x[d] = 0.5f;
-    }
-
-    for (uint32_t level = warp; level < L; level += nwarp) {
-        const uint32_t off = (uint32_t)__ldg(offsets + level);
-        const uint32_t hashmap_size = (uint32_t)__ldg(offsets + level + 1) - off;
-        const float scale = level_scale(level, S, H);
-        const uint32_t resolution = (uint32_t)ceilf(scale) + 1;
-        T* __restrict__ lvl = grad_table + (size_t)off * C;
-
-        T g[C];
-        if (active) {
-            const T* __restrict__ gsrc = level_major ? grad + ((size_t)level * B + b) * C
-                                                     : grad + (size_t)b * F + (size_t)level * C;
-            load_entry<T, C>(gsrc, g);
-        } else {
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) g[c] = from_f<T>(0.f);
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const uint32_t b = tile * TILE_PTS + lane;
+        bool active = b < B;
+        const uint32_t* sg = stage_sm + (it & 1u) * buf_words;
+        const float* sx = reinterpret_cast<const float*>(sg + TILE_PTS * pitch);
+        if (staged) {
+            issue(tile + gridDim.x, (it + 1u) & 1u);
+            cp_async_wait_group<1>();
+            __syncthreads();
         }
 
-        float pos[D];
-        uint32_t pg[D];
+        float x[D];
 #pragma unroll
         for (uint32_t d = 0; d < D; ++d) {
-            pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
-            pg[d] = (uint32_t)floorf(pos[d]);
-            pos[d] -= (float)pg[d];
-            if (interp == 1) pos[d] = smoothstep_f(pos[d]);
+            x[d] = active ? (staged ? sx[lane * D + d] : __ldg(inputs + (size_t)b * D + d)) : 0.5f;
+            if (x[d] < 0 || x[d] > 1) active = false;   // grad_table starts at zero (gridencoder.cu:284-289)
+        }
+        // every warp of the CTA looks at the same 32 points: the skip is CTA-uniform, the barriers stay matched
+        const bool any_active = __ballot_sync(FULL, active) != 0;
+        if (!active) {
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) x[d] = 0.5f;
         }
 
-        uint32_t cidx[1 << D];
-        corner_indices<D>(gridtype, align_corners, hashmap_size, resolution, pg, cidx);
+        for (uint32_t level = warp; any_active && level < L; level += nwarp) {
+            const BwdLevel P = fixed_level ? P_fixed : make_bwd_level<D>(offsets, level, S, H, gridtype, align_corners);
+            const uint32_t off = P.off;
+            const float scale = P.scale;
+            T* __restrict__ lvl = grad_table + (size_t)off * C;
 
-        // ---- run structure of this level, shared by all 2^D corners: consecutive lanes in the SAME CELL have
-        // identical corner indices.  (Inactive lanes are isolated so that a run always ends on an active lane.)
-        // NOTE: no short-circuit '&&' here — every lane must execute every shuffle
-        bool same = active;
+            T g[C];
+            if (active) {
+                if (staged) {
+                    if constexpr (EW > 0) {
+                        uint32_t* gw = reinterpret_cast<uint32_t*>(g);
 #pragma unroll
-        for (uint32_t d = 0; d < D; ++d) {
-            const uint32_t prev_pg = __shfl_up_sync(FULL, pg[d], 1);
-            same = same & (prev_pg == pg[d]);
-        }
-        const int prev_active = __shfl_up_sync(FULL, (int)active, 1);
-        same = same & (prev_active != 0);
-        const bool head = (lane == 0) || !same;
-        const uint32_t heads = __ballot_sync(FULL, head);
-        const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
-        const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
-        const bool issue = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
-
-        // vector reductions address relative to the level base: the level's first entry must itself be suitably aligned
-        // (always true for tables built by GridEncoder: offsets are multiples of 8 entries, grid.py:124)
-        const bool pair_lvl = (off & 1u) == 0u, quad_lvl = quad_ok && (off & 3u) == 0u;
-        (void)pair_lvl; (void)quad_lvl;
-        if constexpr (C == 2) {
-            // corners 2j and 2j+1 differ only in x.  When their entries are an aligned adjacent pair (dense level with an
-            // even base index; hashed level with an even x) both are updated by ONE vector reduction (f16x4 / f32x4):
-            // 25 % fewer L2 reduction ops on average.
-#pragma unroll
-            for (uint32_t j = 0; j < (1u << (D - 1)); ++j) {
-                float wyz = 1;
-#pragma unroll
-                for (uint32_t d = 1; d < D; ++d) wyz *= (((2 * j) & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
-                // same multiplication order as the reference: ((1 * a0) * a1) * a2
-                float w0 = 1 - pos[0], w1 = pos[0];
-#pragma unroll
-                for (uint32_t d = 1; d < D; ++d) {
-                    const float f = (((2 * j) & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
-                    w0 *= f; w1 *= f;
-                }
-                (void)wyz;
-                float v0[2] = {w0 * to_f(g[0]), w0 * to_f(g[1])}, v1[2] = {w1 * to_f(g[0]), w1 * to_f(g[1])};
-                for (uint32_t o = 1; o < maxrun; o <<= 1) {
-#pragma unroll
-                    for (uint32_t c = 0; c < 2; ++c) {
-                        const float t0 = __shfl_up_sync(FULL, v0[c], o), t1 = __shfl_up_sync(FULL, v1[c], o);
-                        if (lane >= my_head + o) { v0[c] += t0; v1[c] += t1; }
+                        for (uint32_t k = 0; k < EW; ++k) gw[k] = sg[lane * pitch + level * EW + k];
                     }
-                }
-                if (issue) {
-                    const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
-                    const bool pair = ((i0 ^ i1) == 1u) && pair_lvl;
-                    if constexpr (sizeof(T) == 2) {
-                        const __half2 h0 = __floats2half2_rn(v0[0], v0[1]), h1 = __floats2half2_rn(v1[0], v1[1]);
-                        if (quad_lvl && !pair && (i0 ^ i1) < 4u) {
-                            // x and x+1 fall into the same aligned quad of entries without being an aligned pair (x odd on a hashed
-                            // level: idx(x) ^ idx(x+1) = 3; dense level with idx % 4 == 1): one 16-byte reduction, the two untouched
-                            // entries receive +0.  Together with the pair case this covers 3 of 4 x-pairs with a single REDG.
-                            const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
-                            const uint32_t a0 = i0 & 3u, a1 = i1 & 3u;
-                            red_add_h8(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~3u) * 2),
-                                       (a0 == 0u ? u0 : 0u) | (a1 == 0u ? u1 : 0u), (a0 == 1u ? u0 : 0u) | (a1 == 1u ? u1 : 0u),
-                                       (a0 == 2u ? u0 : 0u) | (a1 == 2u ? u1 : 0u), (a0 == 3u ? u0 : 0u) | (a1 == 3u ? u1 : 0u));
-                        } else if (pair) {
-                            red_add_h4(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~1u) * 2), (i0 < i1) ? h0 : h1, (i0 < i1) ? h1 : h0);
-                        } else {
-                            red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i0 * 2), h0);
-                            red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i1 * 2), h1);
-                        }
-                    } else {
-                        if (pair) {
-                            float* dst = reinterpret_cast<float*>(lvl + (size_t)(i0 & ~1u) * 2);
-                            if (i0 < i1) red_add_f4(dst, v0[0], v0[1], v1[0], v1[1]);
-                            else red_add_f4(dst, v1[0], v1[1], v0[0], v0[1]);
-                        } else {
-                            red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i0 * 2), v0[0], v0[1]);
-                            red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i1 * 2), v1[0], v1[1]);
-                        }
-                    }
-                }
-            }
-            continue;
-        }
-#pragma unroll
-        for (uint32_t idx = 0; idx < (1u << D); ++idx) {
-            float w = 1;
-#pragma unroll
-            for (uint32_t d = 0; d < D; ++d) w *= ((idx & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
-            const uint32_t index = cidx[idx];
-
-            // addends in fp32; segmented inclusive scan over the run, only as deep as the longest run
-            float v[C];
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) v[c] = w * to_f(g[c]);
-            for (uint32_t o = 1; o < maxrun; o <<= 1) {
-#pragma unroll
-                for (uint32_t c = 0; c < C; ++c) {
-                    const float t = __shfl_up_sync(FULL, v[c], o);
-                    if (lane >= my_head + o) v[c] += t;
-                }
-            }
-            if (issue) {
-                T* dst = lvl + (size_t)index * C;
-                if constexpr (sizeof(T) == 2 && (C % 2 == 0)) {
-#pragma unroll
-                    for (uint32_t c = 0; c < C; c += 2) {
-                        __half2 hv;
-                        hv.x = __float2half_rn(v[c]);
-                        hv.y = __float2half_rn(v[c + 1]);
-                        red_add_h2(reinterpret_cast<__half*>(dst + c), hv);
-                    }
-                } else if constexpr (sizeof(T) == 2) {
-                    // C == 1 half: scalar f16 reduction (the reference's path for this case is a stub)
-                    atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(v[0]));
-                } else if constexpr (C % 2 == 0) {
-#pragma unroll
-                    for (uint32_t c = 0; c < C; c += 2) red_add_f2(reinterpret_cast<float*>(dst + c), v[c], v[c + 1]);
                 } else {
-                    red_add_f1(reinterpret_cast<float*>(dst), v[0]);
+                    const T* __restrict__ gsrc = level_major ? grad + ((size_t)level * B + b) * C
+                                                             : grad + (size_t)b * F + (size_t)level * C;
+                    load_entry<T, C>(gsrc, g);
+                }
+            } else {
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) g[c] = from_f<T>(0.f);
+            }
+
+            float pos[D];
+            uint32_t pg[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                pos[d] = fmaf(x[d], scale, align_corners ? 0.0f : 0.5f);
+                pg[d] = (uint32_t)floorf(pos[d]);
+                pos[d] -= (float)pg[d];
+                if (interp == 1) pos[d] = smoothstep_f(pos[d]);
+            }
+
+            uint32_t cidx[1 << D];
+            corner_indices_mode<D>(P, gridtype, align_corners, pg, cidx);
+
+            // ---- run structure of this level, shared by all 2^D corners: consecutive lanes in the SAME CELL have
+            // identical corner indices.  (Inactive lanes are isolated so that a run always ends on an active lane.)
+            // NOTE: no short-circuit '&&' here — every lane must execute every shuffle
+            bool same = active;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                const uint32_t prev_pg = __shfl_up_sync(FULL, pg[d], 1);
+                same = same & (prev_pg == pg[d]);
+            }
+            const int prev_active = __shfl_up_sync(FULL, (int)active, 1);
+            same = same & (prev_active != 0);
+            const bool head = (lane == 0) || !same;
+            const uint32_t heads = __ballot_sync(FULL, head);
+            const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
+            const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
+            const bool issue_red = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
+
+            if constexpr (C == 2) {
+                // corners 2j and 2j+1 differ only in x.  When their entries are an aligned adjacent pair (dense level with an
+                // even base index; hashed level with an even x) both are updated by ONE vector reduction (f16x4 / f32x4):
+                // 25 % fewer L2 reduction ops on average.  Vector reductions address relative to the level base: the level's first
+                // entry must itself be suitably aligned (always true for tables built by GridEncoder: offsets are multiples of 8
+                // entries, grid.py:124).  (A 16-byte "quad" form covering x / x+1 inside one aligned group of 4 entries was measured
+                // slower — 1.73 -> 1.80 ms, the selection logic costs more issue slots than the 12 % fewer reductions save — and removed.)
+                const bool pair_lvl = (off & 1u) == 0u;
+#pragma unroll
+                for (uint32_t j = 0; j < (1u << (D - 1)); ++j) {
+                    // same multiplication order as the reference: ((1 * a0) * a1) * a2
+                    float w0 = 1 - pos[0], w1 = pos[0];
+#pragma unroll
+                    for (uint32_t d = 1; d < D; ++d) {
+                        const float f = (((2 * j) & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+                        w0 *= f; w1 *= f;
+                    }
+                    float v0[2] = {w0 * to_f(g[0]), w0 * to_f(g[1])}, v1[2] = {w1 * to_f(g[0]), w1 * to_f(g[1])};
+                    for (uint32_t o = 1; o < maxrun; o <<= 1) {
+#pragma unroll
+                        for (uint32_t c = 0; c < 2; ++c) {
+                            const float t0 = __shfl_up_sync(FULL, v0[c], o), t1 = __shfl_up_sync(FULL, v1[c], o);
+                            if (lane >= my_head + o) { v0[c] += t0; v1[c] += t1; }
+                        }
+                    }
+                    if (issue_red) {
+                        const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
+                        const bool pair = ((i0 ^ i1) == 1u) && pair_lvl;
+                        if constexpr (sizeof(T) == 2) {
+                            const __half2 h0 = __floats2half2_rn(v0[0], v0[1]), h1 = __floats2half2_rn(v1[0], v1[1]);
+                            if (pair) {
+                                red_add_h4(reinterpret_cast<__half*>(lvl + (size_t)(i0 & ~1u) * 2), (i0 < i1) ? h0 : h1, (i0 < i1) ? h1 : h0);
+                            } else {
+                                red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i0 * 2), h0);
+                                red_add_h2(reinterpret_cast<__half*>(lvl + (size_t)i1 * 2), h1);
+                            }
+                        } else {
+                            if (pair) {
+                                float* dst = reinterpret_cast<float*>(lvl + (size_t)(i0 & ~1u) * 2);
+                                if (i0 < i1) red_add_f4(dst, v0[0], v0[1], v1[0], v1[1]);
+                                else red_add_f4(dst, v1[0], v1[1], v0[0], v0[1]);
+                            } else {
+                                red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i0 * 2), v0[0], v0[1]);
+                                red_add_f2(reinterpret_cast<float*>(lvl + (size_t)i1 * 2), v1[0], v1[1]);
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (uint32_t idx = 0; idx < (1u << D); ++idx) {
+                    float w = 1;
+#pragma unroll
+                    for (uint32_t d = 0; d < D; ++d) w *= ((idx & (1u << d)) == 0) ? (1 - pos[d]) : pos[d];
+                    const uint32_t index = cidx[idx];
+
+                    // addends in fp32; segmented inclusive scan over the run, only as deep as the longest run
+                    float v[C];
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) v[c] = w * to_f(g[c]);
+                    for (uint32_t o = 1; o < maxrun; o <<= 1) {
+#pragma unroll
+                        for (uint32_t c = 0; c < C; ++c) {
+                            const float t = __shfl_up_sync(FULL, v[c], o);
+                            if (lane >= my_head + o) v[c] += t;
+                        }
+                    }
+                    if (issue_red) {
+                        T* dst = lvl + (size_t)index * C;
+                        if constexpr (sizeof(T) == 2 && (C % 2 == 0)) {
+#pragma unroll
+                            for (uint32_t c = 0; c < C; c += 2) {
+                                __half2 hv;
+                                hv.x = __float2half_rn(v[c]);
+                                hv.y = __float2half_rn(v[c + 1]);
+                                red_add_h2(reinterpret_cast<__half*>(dst + c), hv);
+                            }
+                        } else if constexpr (sizeof(T) == 2) {
+                            // C == 1 half: scalar f16 reduction (the reference's path for this case is a stub)
+                            atomicAdd(reinterpret_cast<__half*>(dst), __float2half_rn(v[0]));
+                        } else if constexpr (C % 2 == 0) {
+#pragma unroll
+                            for (uint32_t c = 0; c < C; c += 2) red_add_f2(reinterpret_cast<float*>(dst + c), v[c], v[c + 1]);
+                        } else {
+                            red_add_f1(reinterpret_cast<float*>(dst), v[0]);
+                        }
+                    }
                 }
             }
         }
+        if (staged) __syncthreads();       // everybody is done with this buffer before the next iteration's copy lands in it
     }
 }
 
@@ -543,14 +650,16 @@ static int launch_bwd(const void* grad, const float* inputs, const int* offsets,
                       bool ac, uint32_t interp, bool level_major, cudaStream_t st) {
     const uint32_t nw = L < 16 ? L : 16;
     dim3 block(32, nw);
-    dim3 grid(div_up(B, TILE_PTS));
-    // 16-byte quad reductions (x / x+1 in one aligned quad of entries -> one REDG.F16x8) are implemented but OFF: measured on the bench
-    // scene they make the kernel slower (1.73 -> 1.80 ms; ncu r2: the scatter is issue-bound at 74 % issue-slot utilisation and the
-    // quad selection adds ~100 instructions per warp-level, more than the ~12 % fewer reduction ops save).  NGP_GRID_QUAD_RED=1 enables.
-    static const bool quad_env = [] { const char* e = getenv("NGP_GRID_QUAD_RED"); return e && e[0] == '1'; }();
-    const bool quad_ok = quad_env && (reinterpret_cast<uintptr_t>(gemb) & 15u) == 0;
-    k_grid_backward<T, D, C><<<grid, block, 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
-                                                     gridtype, ac, interp, level_major, quad_ok);
+    const uint32_t ntiles = div_up(B, TILE_PTS);
+    const uint32_t cap = (uint32_t)sm_count() * (nw > 8 ? 3u : 6u);      // resident CTAs per SM at 40 registers / thread
+    dim3 grid(ntiles < cap ? ntiles : cap);
+    // staged (cp.async double-buffered) inputs: point-major gradients whose (level, point) entries are whole 32-bit words
+    const uint32_t row_words = (uint32_t)(((size_t)L * C * sizeof(T)) / 4);
+    const size_t smem = 2 * (size_t)(TILE_PTS * (row_words | 1u) + TILE_PTS * D) * 4;
+    static const bool stage_env = [] { const char* e = getenv("NGP_GRID_BWD_STAGED"); return !(e && e[0] == '0'); }();
+    const bool staged = stage_env && !level_major && (C * sizeof(T)) % 4 == 0 && smem <= 40 * 1024;
+    k_grid_backward<T, D, C><<<grid, block, staged ? smem : 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
+                                                                      gridtype, ac, interp, level_major, staged);
     int rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && ginp) {

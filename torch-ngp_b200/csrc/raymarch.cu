@@ -349,11 +349,20 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+struct MseArgs {             // optional loss head of k_composite_train_fwd (target == nullptr: plain compositor)
+    const float* target;     // [N,3] indexed like image
+    float bg, inv_norm;      // background colour; 2 / (3 R)
+    const float* scale;      // device scalar: loss scale
+    float* g_image;          // [N,3] d(scaled loss)/d image
+    float* g_ws;             // [N]   d(scaled loss)/d weights_sum
+    float* sqerr;            // [N]   squared error per row of the rays table
+};
+
 __global__ void __launch_bounds__(128)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                       const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M, uint32_t N,
                       float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth,
-                      float* __restrict__ image) {
+                      float* __restrict__ image, const MseArgs mse) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per row of the rays table
@@ -398,7 +407,28 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     if (lane == 0) {
         weights_sum[index] = ws; depth[index] = d;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
+        if (mse.target) {
+            // loss head of the training step (nerf/utils.py:861-868 with the renderer's background blend, renderer.py:313):
+            // pred = image + (1 - ws) * bg ; loss = mean((pred - target)^2) over 3 R values ; gradients scaled by the loss scale
+            const float k = mse.inv_norm * __ldg(mse.scale);
+            const float bgw = (1.0f - ws) * mse.bg;
+            const float d0 = (r + bgw) - __ldg(mse.target + index * 3), d1 = (g + bgw) - __ldg(mse.target + index * 3 + 1),
+                        d2 = (b + bgw) - __ldg(mse.target + index * 3 + 2);
+            const float g0 = d0 * k, g1 = d1 * k, g2 = d2 * k;
+            mse.g_image[index * 3] = g0; mse.g_image[index * 3 + 1] = g1; mse.g_image[index * 3 + 2] = g2;
+            mse.g_ws[index] = -((g0 + g1) + g2) * mse.bg;
+            mse.sqerr[n] = (d0 * d0 + d1 * d1) + d2 * d2;
+        }
     }
+}
+
+// tail of the marcher in the step driver: the reference's 16-slot sample-count ring (renderer.py:281-283), advanced on the device
+__global__ void k_step_counter_push(int* __restrict__ ring, const int* __restrict__ counter, int* __restrict__ nsteps,
+                                    int* __restrict__ step_counter) {
+    const int r = ring[0] & 15;
+    step_counter[2 * r] = counter[0]; step_counter[2 * r + 1] = counter[1];
+    ring[0] = (r + 1) & 15;
+    nsteps[0] += 1;
 }
 
 __global__ void __launch_bounds__(128)
@@ -692,7 +722,28 @@ extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float
                                                 ngp_stream_t stream) {
     if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_forward: too many rays");
     NGP_LAUNCH_1D(k_composite_train_fwd, N * 32, 128, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
-                  T_thresh, weights_sum, depth, image);
+                  T_thresh, weights_sum, depth, image, MseArgs{});
+}
+// Compositor + loss head in one launch (extension used by the step driver): additionally forms pred = image + (1 - ws) * bg,
+// the squared error per ray (sqerr [N], row order of `rays`) and d(loss * *scale)/d(image, ws) for loss = sum(sqerr) * inv_norm / 2,
+// i.e. inv_norm = 2 / (3 R) for the mean over 3 R values.  Replaces ~12 elementwise / reduction launches of the torch expression.
+extern "C" int ngp_composite_rays_train_forward_mse(const float* sigmas, const float* rgbs, const float* deltas,
+                                                    const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                                    const float* target, float bg, float inv_norm, const float* scale,
+                                                    float* weights_sum, float* depth, float* image, float* g_image, float* g_ws,
+                                                    float* sqerr, ngp_stream_t stream) {
+    if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_forward_mse: too many rays");
+    if (!target || !scale || !g_image || !g_ws || !sqerr) return fail(NGP_EINVAL, "composite_rays_train_forward_mse: null pointer");
+    MseArgs mse{target, bg, inv_norm, scale, g_image, g_ws, sqerr};
+    NGP_LAUNCH_1D(k_composite_train_fwd, N * 32, 128, "composite_rays_train_forward_mse", sigmas, rgbs, deltas, rays, M, N,
+                  T_thresh, weights_sum, depth, image, mse);
+}
+// ring [1] i32 (next row), counter [2] i32 (this march's totals), nsteps [1] i32, step_counter [16,2] i32
+extern "C" int ngp_step_counter_push(int32_t* ring, const int32_t* counter, int32_t* nsteps, int32_t* step_counter,
+                                     ngp_stream_t stream) {
+    if (!ring || !counter || !nsteps || !step_counter) return fail(NGP_EINVAL, "step_counter_push: null pointer");
+    k_step_counter_push<<<1, 1, 0, as_stream(stream)>>>(ring, counter, nsteps, step_counter);
+    return check_launch("step_counter_push");
 }
 extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
                                                  const float* sigmas, const float* rgbs, const float* deltas,

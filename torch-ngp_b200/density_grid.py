@@ -92,7 +92,7 @@ def fused_density_fn(model):
         M = x01.shape[0]
         sigma = torch.empty(M, dtype=torch.float32, device=x.device)
         table = _half_table(enc.embeddings)
-        w = net.weights.detach().half().contiguous()
+        w = _half_table(net.weights).contiguous()      # owner-maintained fp16 copy when the fused optimizer holds one
         L = enc.offsets.shape[0] - 1
         _backend.call("ngp_field_sigma_forward", x01.data_ptr(), table.data_ptr(), enc.offsets.data_ptr(), L, float(np.log2(pls)),
                       int(base), gridtype, int(align), w.data_ptr(), nl_s, M, 0, None, None, None, sigma.data_ptr())

@@ -18,7 +18,7 @@ from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
 import _ngp_b200 as _backend
-from ngp_autograd import _half_table
+from ngp_autograd import _half_table, _half_param
 
 WGRAD_ACCUMULATE, WGRAD_NO_FINALIZE = 1, 2
 DEFAULT_CHUNKS = 1          # autograd path (fused_field); the step driver passes its own chunk count
@@ -44,8 +44,8 @@ def field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg, chunks
     x01 = ((xyzs.float() + bound) / (2 * bound)).contiguous()       # GridEncoder.forward's affine map (grid.py:149)
     dirs = dirs.float().contiguous()
     table = _half_table(embeddings)
-    ws = sigma_w.detach().half().contiguous()
-    wc = color_w.detach().half().contiguous()
+    ws = _half_param(sigma_w)          # the optimizer's fp16 operand copy when it owns one, else a cast (ffmlp.py:18)
+    wc = _half_param(color_w)
     M = x01.shape[0]
     L = offsets.shape[0] - 1
     S = float(np.log2(pls))

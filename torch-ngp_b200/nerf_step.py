@@ -209,7 +209,7 @@ class FusedTrainStep:
         self._side = None               # field pipelining stream
         self._march_stream = None       # prefetch stream (lowest priority)
         dev = model.density_bitfield.device
-        self._ring = torch.zeros(1, dtype=torch.long, device=dev)        # next row of model.step_counter (device side)
+        self._ring = torch.zeros(1, dtype=torch.int32, device=dev)       # next row of model.step_counter (device side)
         self._nsteps = torch.zeros(1, dtype=torch.int32, device=dev)     # steps since the last sync_host_state()
 
     # ---- sample generation -------------------------------------------------------------------------------------------------
@@ -229,9 +229,14 @@ class FusedTrainStep:
         if s is None or s["M"] != M or s["N"] != n_rays:
             dev = m.density_bitfield.device
             f = dict(dtype=torch.float32, device=dev)
-            s = dict(M=M, N=n_rays, xyzs=torch.zeros(M, 3, **f), dirs=torch.zeros(M, 3, **f), deltas=torch.zeros(M, 2, **f),
+            # xyzs | dirs | deltas | counter share one allocation: one memset per march instead of four
+            flat = torch.zeros(M * 8 + 2, **f)
+            s = dict(M=M, N=n_rays, flat=flat, xyzs=flat[:M * 3].view(M, 3), dirs=flat[M * 3:M * 6].view(M, 3),
+                     deltas=flat[M * 6:M * 8].view(M, 2), counter=flat[M * 8:].view(torch.int32),
                      rays=torch.zeros(n_rays, 3, dtype=torch.int32, device=dev), nears=torch.empty(n_rays, **f),
-                     fars=torch.empty(n_rays, **f), counter=torch.zeros(2, dtype=torch.int32, device=dev))
+                     fars=torch.empty(n_rays, **f),
+                     # composite / loss scratch of the step that consumes these samples
+                     grads=torch.zeros(M, 4, **f), per_ray=torch.empty(n_rays, 13, **f))
             self._slots[i] = s
         return s
 
@@ -247,16 +252,14 @@ class FusedTrainStep:
         nb.call("ngp_near_far_from_aabb", o.data_ptr(), d.data_ptr(), m.aabb_train.data_ptr(), n, float(m.min_near),
                 s["nears"].data_ptr(), s["fars"].data_ptr())
         # rows the marcher does not reach must read as zeros (raymarching.py:205-207)
-        s["xyzs"].zero_(); s["dirs"].zero_(); s["deltas"].zero_(); s["counter"].zero_()
+        s["flat"].zero_()
         noise = torch.rand(n, dtype=torch.float32, device=o.device) if self.perturb else torch.zeros(n, dtype=torch.float32, device=o.device)
         nb.call("ngp_march_rays_train", o.data_ptr(), d.data_ptr(), m.density_bitfield.data_ptr(), float(m.bound), float(self.dt_gamma),
                 int(self.max_steps), n, int(m.cascade), int(m.grid_size), s["M"], s["nears"].data_ptr(), s["fars"].data_ptr(),
                 s["xyzs"].data_ptr(), s["dirs"].data_ptr(), s["deltas"].data_ptr(), s["rays"].data_ptr(), s["counter"].data_ptr(),
                 noise.data_ptr())
         # the reference's 16-slot sample-count ring (renderer.py:281-283), advanced on the device
-        m.step_counter.index_copy_(0, self._ring, s["counter"].view(1, 2))
-        self._ring.add_(1).remainder_(16)
-        self._nsteps.add_(1)
+        nb.call("ngp_step_counter_push", self._ring.data_ptr(), s["counter"].data_ptr(), self._nsteps.data_ptr(), m.step_counter.data_ptr())
         self._ready[i] = True
 
     @torch.no_grad()
@@ -308,20 +311,23 @@ class FusedTrainStep:
         if m.density_scale != 1:
             sigma = sigma * m.density_scale
         M, N = sigma.shape[0], s["N"]
-        dev = sigma.device
         deltas, rays = s["deltas"], s["rays"]
-        wsum = torch.empty(N, device=dev); depth = torch.empty(N, device=dev); image = torch.empty(N, 3, device=dev)
-        nb.call("ngp_composite_rays_train_forward", sigma.data_ptr(), rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), M, N,
-                float(self.T_thresh), wsum.data_ptr(), depth.data_ptr(), image.data_ptr())
-        pred = image + (1 - wsum).unsqueeze(-1) * self.bg
-        diff = pred - target
-        loss = (diff * diff).sum() / (3.0 * self.R)
-        # d loss / d pred, scaled by the device-resident loss scale
-        g_pred = (diff * ((2.0 / (3.0 * self.R)) * self.opt.scale_tensor())).contiguous()
-        g_ws = (-(g_pred.sum(-1)) * self.bg).contiguous()
-        g_sigma = torch.zeros(M, device=dev); g_rgb = torch.zeros(M, 3, device=dev)
-        nb.call("ngp_composite_rays_train_backward", g_ws.data_ptr(), g_pred.data_ptr(), sigma.data_ptr(),
-                rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), wsum.data_ptr(), image.data_ptr(), M, N, float(self.T_thresh),
+        target = target.reshape(-1, 3).float().contiguous()
+        assert target.shape[0] == N, "one target colour per ray"
+        # per-ray scratch [N,13]: wsum | depth | image(3) | g_image(3) | g_ws | sqerr | (3 spare)
+        pr = s["per_ray"]
+        base = pr.data_ptr()
+        wsum_p, depth_p, image_p, gimg_p, gws_p, sq_p = base, base + 4 * N, base + 8 * N, base + 20 * N, base + 32 * N, base + 36 * N
+        # compositor + loss head in one launch: pred = image + (1 - ws) bg, squared error per ray, d(scaled loss)/d(image, ws)
+        nb.call("ngp_composite_rays_train_forward_mse", sigma.data_ptr(), rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), M, N,
+                float(self.T_thresh), target.data_ptr(), float(self.bg), float(2.0 / (3.0 * self.R)), self.opt.scale_tensor().data_ptr(),
+                wsum_p, depth_p, image_p, gimg_p, gws_p, sq_p)
+        loss = pr.view(-1)[9 * N:10 * N].sum() * (1.0 / (3.0 * self.R))
+        grads = s["grads"]
+        grads.zero_()                                     # samples behind a ray's termination point receive no gradient
+        g_rgb, g_sigma = grads.view(-1)[:3 * M].view(M, 3), grads.view(-1)[3 * M:]
+        nb.call("ngp_composite_rays_train_backward", gws_p, gimg_p, sigma.data_ptr(),
+                rgb.data_ptr(), deltas.data_ptr(), rays.data_ptr(), wsum_p, image_p, M, N, float(self.T_thresh),
                 g_sigma.data_ptr(), g_rgb.data_ptr())
         if m.density_scale != 1:
             g_sigma = g_sigma * m.density_scale
@@ -411,7 +417,7 @@ class EvalRenderer:
     def __call__(self, rays_o, rays_d, bg_color=1.0):
         import _ngp_b200 as nb
         from nerf_fused import field_cfg
-        from ngp_autograd import _half_table
+        from ngp_autograd import _half_table, _half_param
         m, N = self.m, self.N
         assert self.block % 2 == 0, "an even block keeps the alive-list ping-pong aligned across replays"
         field_cfg(m.encoder, m.sigma_net, m.color_net, m.bound, False)       # validates the topology
@@ -420,12 +426,12 @@ class EvalRenderer:
         table = _half_table(m.encoder.embeddings)
         if getattr(self, "_table", None) is None or self._table.shape != table.shape:
             self._table = table.clone() if table is not getattr(m.encoder.embeddings, "_ngp_half_shadow", None) else table
-            self._ws = m.sigma_net.weights.detach().half().contiguous()
-            self._wc = m.color_net.weights.detach().half().contiguous()
+            self._ws = _half_param(m.sigma_net.weights).clone()
+            self._wc = _half_param(m.color_net.weights).clone()
         else:
             if self._table is not table:
                 self._table.copy_(table)
-            self._ws.copy_(m.sigma_net.weights.detach()); self._wc.copy_(m.color_net.weights.detach())
+            self._ws.copy_(_half_param(m.sigma_net.weights)); self._wc.copy_(_half_param(m.color_net.weights))
         nb.call("ngp_near_far_from_aabb", self.rays_o.data_ptr(), self.rays_d.data_ptr(), m.aabb_train.data_ptr(), N, float(m.min_near),
                 self.nears.data_ptr(), self.fars.data_ptr())
         self.rays_t.copy_(self.nears)

@@ -39,8 +39,15 @@ def _half_table(embeddings):
     return embeddings.detach().to(torch.half)
 
 
-def own_half_table(embeddings):
-    """Install (or refresh) the owner-maintained fp16 shadow of `embeddings`; returns it."""
+def own_half_table(embeddings, into=None):
+    """Install (or refresh) the owner-maintained fp16 shadow of `embeddings`; returns it.  `into` (optional): a half tensor of the
+    parameter's shape that becomes the shadow (the fused optimizer keeps all shadows in one flat, peer-visible buffer)."""
+    if into is not None:
+        assert into.shape == embeddings.shape and into.dtype == torch.half and into.device == embeddings.device
+        with torch.no_grad():
+            into.copy_(embeddings.detach())
+        embeddings._ngp_half_shadow = into
+        return into
     hit = getattr(embeddings, "_ngp_half_shadow", None)
     if hit is not None and hit.shape == embeddings.shape and hit.device == embeddings.device:
         hit.copy_(embeddings.detach())
@@ -48,6 +55,12 @@ def own_half_table(embeddings):
     half = embeddings.detach().to(torch.half)
     embeddings._ngp_half_shadow = half
     return half
+
+
+def _half_param(p):
+    """fp16 kernel operand of any hot-path parameter (hash table or flat FFMLP weight vector): the owner-maintained shadow when one
+    exists (always current, see _half_table), otherwise a fresh cast as the reference does (ffmlp.py:18 custom_fwd cast)."""
+    return _half_table(p).contiguous()
 
 
 def invalidate_half_table(embeddings):

@@ -98,3 +98,129 @@ def seed_unlock(states):
     if cuda_state is not None:
         torch.cuda.set_rng_state(cuda_state)
 
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory exchange
+def shard_bounds(n, world, align=8):
+    """Flat-parameter shards for the fused exchange + optimizer (csrc/exchange.cu): `world` contiguous ranges covering [0, n) whose
+    boundaries are multiples of `align` elements (n itself must be).  Returns [lo_0, lo_1, ..., lo_world = n]."""
+    if n % align:
+        raise ValueError(f"shard_bounds: n = {n} is not a multiple of {align}")
+    units = n // align
+    base, rem = divmod(units, world)
+    out = [0]
+    for r in range(world):
+        out.append(out[-1] + (base + (1 if r < rem else 0)) * align)
+    return out
+
+
+def segment_pieces(segments, lo, hi):
+    """Intersection of the flat range [lo, hi) with parameter segments [(off, count), ...]: [(segment index, piece_lo, piece_count)]."""
+    out = []
+    for i, (off, cnt) in enumerate(segments):
+        a, b = max(lo, off), min(hi, off + cnt)
+        if b > a:
+            out.append((i, a, b - a))
+    return out
+
+
+class _RawCuda:
+    """Device memory owned by libngp_b200 (cudaMalloc / CUDA IPC mapping), exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class PeerExchange:
+    """Peer-visible buffers of every rank of one node, for the fused gradient exchange + optimizer (csrc/exchange.cu).
+
+    Each rank allocates ONE block through the library (ngp_peer_alloc: cudaMalloc + CUDA IPC handle) holding
+        [ signal pad 16 KB | fp16 gradient sink (n) | fp16 operand shadow (n) ]
+    the 64-byte handles travel through torch.distributed (all_gather_object — plumbing), and every rank maps the other ranks' blocks
+    (ngp_peer_open, peer access over NVLink).  `sink` / `shadow` are torch views of the LOCAL block; `pads` / `sinks` / `shadows` are
+    host arrays of the per-rank device pointers as mapped in this process, handed to the exchange kernels by value."""
+
+    def __init__(self, n_elems, group=None, device=None):
+        import ctypes
+        import _ngp_b200 as nb
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n = int(n_elems)
+        if self.n % 8:
+            raise ValueError("PeerExchange: element count must be a multiple of 8")
+        if self.world > 16:
+            raise RuntimeError("PeerExchange: at most 16 ranks per node")
+        lib = nb.load()
+        self._lib = lib
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        pad = int(lib.ngp_exchange_pad_bytes())
+        seg = (2 * self.n + 255) // 256 * 256
+        self._pad_bytes, self._seg_bytes = pad, seg
+        total = pad + 2 * seg
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(dev):
+            rc = lib.ngp_peer_alloc(total, ctypes.byref(ptr), handle)
+            if rc != 0:
+                raise RuntimeError(f"ngp_peer_alloc failed ({rc}): {lib.ngp_last_error().decode()}")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (bytes(handle.raw), int(dev.index)), group=group)
+            self._base = [None] * self.world
+            self._base[self.rank] = int(ptr.value)
+            for r, (h, _) in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = ctypes.c_void_p()
+                rc = lib.ngp_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p))
+                if rc != 0:
+                    raise RuntimeError(f"ngp_peer_open(rank {r}) failed ({rc}): {lib.ngp_last_error().decode()}")
+                self._base[r] = int(p.value)
+        arr = ctypes.c_void_p * self.world
+        self.pads = arr(*[b for b in self._base])
+        self.sinks = arr(*[b + pad for b in self._base])
+        self.shadows = arr(*[b + pad + seg for b in self._base])
+        self._raw = (_RawCuda(self._base[self.rank] + pad, self.n, "<f2"), _RawCuda(self._base[self.rank] + pad + seg, self.n, "<f2"))
+        self.sink = torch.as_tensor(self._raw[0], device=dev)
+        self.shadow = torch.as_tensor(self._raw[1], device=dev)
+        assert self.sink.data_ptr() == self._base[self.rank] + pad and self.sink.dtype == torch.half
+        self.bounds = shard_bounds(self.n, self.world)
+        dist.barrier(group=group)        # every rank has mapped every block before anyone signals into it
+
+    @property
+    def my_range(self):
+        return self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    def barrier(self, slot, flag_in=None, flag_out=None, timeout_ms=20000):
+        import _ngp_b200 as nb
+        nb.call("ngp_exchange_barrier", self.pads, self.rank, self.world, int(slot), flag_in, flag_out, int(timeout_ms))
+
+    def error(self):
+        """Non-zero when a barrier timed out (1 + slot).  Host read: synchronises."""
+        import ctypes
+        torch.cuda.synchronize(self.device)
+        out = ctypes.c_uint32(0)
+        rc = self._lib.ngp_exchange_error(ctypes.c_void_p(self._base[self.rank]), ctypes.byref(out))
+        if rc != 0:
+            raise RuntimeError(f"ngp_exchange_error failed: {self._lib.ngp_last_error().decode()}")
+        return int(out.value)
+
+    def close(self):
+        """Unmap the peers' blocks and free the local one (after a barrier: nobody may still be signalling into it)."""
+        if getattr(self, "_base", None) is None:
+            return
+        import ctypes
+        torch.cuda.synchronize(self.device)
+        try:
+            dist.barrier(group=self.group)
+        except Exception:
+            pass
+        for r, b in enumerate(self._base):
+            if r != self.rank and b:
+                self._lib.ngp_peer_close(ctypes.c_void_p(b))
+        self.sink = self.shadow = None
+        self._lib.ngp_peer_free(ctypes.c_void_p(self._base[self.rank]))
+        self._base = None

@@ -172,7 +172,7 @@ class _GridMLPFn(Function):
         bound, pls, H, gridtype, align, nl, out_dim, inference = cfg
         x01 = ((coords.float() + bound) / (2 * bound)).contiguous().view(-1, 3)      # GridEncoder.forward's affine map (grid.py:149)
         table = _half_table(embeddings)
-        w = weights.detach().half().contiguous()
+        w = _half_table(weights).contiguous()          # owner-maintained fp16 copy when the fused optimizer holds one, else a cast
         M, L, S, dev = x01.shape[0], offsets.shape[0] - 1, float(np.log2(pls)), x01.device
         h = torch.empty(M, 16, dtype=torch.half, device=dev)
         feat = fb = None
@@ -243,7 +243,7 @@ class _ColorMLPFn(Function):
         nl, out_dim, inference = cfg
         d = dirs.float().contiguous()
         p = pad.half().contiguous().view(-1)
-        w = weights.detach().half().contiguous()
+        w = _half_table(weights).contiguous()          # owner-maintained fp16 copy when the fused optimizer holds one, else a cast
         M, dev = d.shape[0], d.device
         h_ptr = _rows_of_16(geo)
         y = torch.empty(M, 16, dtype=torch.half, device=dev)

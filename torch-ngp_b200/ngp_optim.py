@@ -12,25 +12,54 @@ import torch.distributed as dist
 
 import _ngp_b200 as _backend
 from ngp_autograd import own_half_table, invalidate_half_table
+from ngp_dp import segment_pieces
 
 
 class FusedFieldOptimizer:
+    """exchange="auto": at world size > 1 the gradient exchange runs over NVLink peer memory fused with a SHARDED optimizer pass
+    (csrc/exchange.cu through ngp_dp.PeerExchange: reduce-scatter by peer loads, Adam on 1/world of the parameters, fp16 operand copies
+    stored into every replica); "nccl": one NCCL all-reduce of the fp16 sink and the full optimizer pass on every rank (the baseline);
+    with the peer path the fp32 masters / moments of the other ranks' shards are stale until gather_master()."""
+
     def __init__(self, encoder, sigma_net, color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=65536.0,
-                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+                 growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, exchange="auto", group=None):
         self.encoder = encoder
         self.params = [encoder.embeddings, sigma_net.weights, color_net.weights]
         dev = self.params[0].device
         self.lr, self.betas, self.eps = lr, betas, eps
         self.growth, self.backoff, self.growth_interval = growth_factor, backoff_factor, growth_interval
         n = sum(p.numel() for p in self.params)
-        self.sink = torch.zeros(n, dtype=torch.half, device=dev)            # flat fp16 gradient bucket
+        self.group = group
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        assert exchange in ("auto", "peer", "nccl")
+        self.px = None
+        if world > 1 and exchange in ("auto", "peer") and dev.type == "cuda":
+            try:
+                from ngp_dp import PeerExchange
+                self.px = PeerExchange(n, group=group, device=dev)
+            except Exception as e:          # no peer access between the ranks' devices (or not one node): NCCL carries the exchange
+                if exchange == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"FusedFieldOptimizer: peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                self.px = None
+            if world > 1:
+                # every rank must have taken the same decision
+                ok = torch.tensor([1 if self.px is not None else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if int(ok.item()) == 0 and self.px is not None:
+                    self.px.close()
+                    self.px = None
+        if self.px is not None:
+            self.sink, self.shadow_flat = self.px.sink, self.px.shadow        # views of the peer-visible block
+        else:
+            self.sink = torch.zeros(n, dtype=torch.half, device=dev)          # flat fp16 gradient bucket
+            self.shadow_flat = torch.zeros(n, dtype=torch.half, device=dev)   # flat fp16 operand copies (hash table, MLP weights)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.state = torch.zeros(8, dtype=torch.int32, device=dev)          # {scale, growth_tracker, found_inf, step, lr_scale, -, -, -}
         self.state[0:1].view(torch.float32).fill_(init_scale)
         self.state[4:5].view(torch.float32).fill_(1.0)
-        # the fp16 kernel operand of the hash table is owned here: the Adam kernel rewrites it with every update
-        self.shadow = own_half_table(encoder.embeddings)
         self._exchange = None
         self.segments = []
         off = 0
@@ -38,8 +67,16 @@ class FusedFieldOptimizer:
             k = p.numel()
             view = self.sink[off:off + k].view_as(p)
             p._ngp_grad_sink = view          # nerf_fused writes its fp16 gradients straight into this view
+            # the fp16 kernel operand of every parameter is owned here: the Adam kernel rewrites it with every update
+            own_half_table(p, into=self.shadow_flat[off:off + k].view_as(p))
             self.segments.append((p, off, k))
             off += k
+        self.shadow = self.encoder.embeddings._ngp_half_shadow
+        if self.px is not None:
+            lo, hi = self.px.my_range
+            self._pieces = segment_pieces([(o, k) for _, o, k in self.segments], lo, hi)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)        # all shadows initialised before any rank's first exchange writes into them
 
     def scale_tensor(self):
         """Device scalar holding the current loss scale: `(loss * opt.scale_tensor()).backward()`."""
@@ -50,14 +87,18 @@ class FusedFieldOptimizer:
         self.state[4:5].view(torch.float32).fill_(float(factor))
 
     def refresh_shadow(self):
-        """Call after anything else wrote the hash table (`.data` writes such as EMA copy_to()/restore(), load_state_dict)."""
-        self.shadow = own_half_table(self.encoder.embeddings)
+        """Call after anything else wrote the parameters (`.data` writes such as EMA copy_to()/restore(), load_state_dict)."""
+        for p, off, k in self.segments:
+            own_half_table(p, into=self.shadow_flat[off:off + k].view_as(p))
 
     def detach(self):
         for p in self.params:
             if hasattr(p, "_ngp_grad_sink"):
                 del p._ngp_grad_sink
-        invalidate_half_table(self.encoder.embeddings)
+            invalidate_half_table(p)
+        if self.px is not None:
+            self.px.close()
+            self.px = None
 
     @torch.no_grad()
     def _absorb_autograd_grads(self):
@@ -69,10 +110,12 @@ class FusedFieldOptimizer:
                 p.grad = None
 
     def begin_exchange(self, group=None):
-        """Launch the step's only exchange (sum-allreduce of the fp16 sink) without blocking the current stream: NCCL runs it on
-        its own stream after the work queued so far; finish_exchange() makes the current stream wait for it."""
+        """NCCL path: launch the step's only exchange (sum-allreduce of the fp16 sink) without blocking the current stream: NCCL runs it
+        on its own stream after the work queued so far; finish_exchange() makes the current stream wait for it.  Peer path: nothing to
+        start — the exchange is part of apply()."""
         self._absorb_autograd_grads()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        group = group if group is not None else self.group
+        if self.px is None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             self._exchange = dist.all_reduce(self.sink, op=dist.ReduceOp.SUM, group=group, async_op=True)
 
     def finish_exchange(self):
@@ -89,22 +132,58 @@ class FusedFieldOptimizer:
 
     @torch.no_grad()
     def apply(self):
-        """inf check + Adam + fp16 shadow refresh + gradient zeroing + GradScaler update on the (already reduced) sink."""
+        """inf check + Adam + fp16 shadow refresh + gradient zeroing + GradScaler update; on the peer path preceded by the reduction
+        of this rank's shard and followed by the stores into every replica's shadow."""
+        if self.px is not None:
+            return self._apply_peer()
         _backend.call("ngp_optim_check_finite", self.sink.data_ptr(), 1, self.sink.numel(), self.state.data_ptr())
         for p, off, k in self.segments:
-            shadow = self.shadow if p is self.encoder.embeddings else None    # refreshed in place by the kernel
             _backend.call("ngp_optim_adam_step", p.data_ptr(), self.exp_avg.data_ptr() + 4 * off,
-                          self.exp_avg_sq.data_ptr() + 4 * off, self.sink.data_ptr() + 2 * off, 1, _backend.ptr(shadow), k,
+                          self.exp_avg_sq.data_ptr() + 4 * off, self.sink.data_ptr() + 2 * off, 1, self.shadow_flat.data_ptr() + 2 * off, k,
                           float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                           self.state.data_ptr(), 1)
         _backend.call("ngp_optim_scaler_update", self.state.data_ptr(), float(self.growth), float(self.backoff),
                       int(self.growth_interval))
+
+    def _apply_peer(self):
+        px = self.px
+        lo, hi = px.my_range
+        found = self.state.data_ptr() + 8          # &state.found_inf
+        px.barrier(0)
+        _backend.call("ngp_exchange_reduce", px.sinks, px.rank, px.world, lo, hi - lo, self.state.data_ptr())
+        px.barrier(1, found, found)
+        for i, a, cnt in self._pieces:
+            p, off, _ = self.segments[i]
+            _backend.call("ngp_exchange_adam", p.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.sink.data_ptr(),
+                          px.shadows, px.world, off, a, cnt, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                          float(self.eps), self.state.data_ptr())
+        _backend.call("ngp_exchange_zero", self.sink.data_ptr(), self.sink.numel())
+        px.barrier(2)
+        _backend.call("ngp_optim_scaler_update", self.state.data_ptr(), float(self.growth), float(self.backoff),
+                      int(self.growth_interval))
+
+    @torch.no_grad()
+    def gather_master(self):
+        """Peer path: every rank updates only its own shard of the fp32 masters and moments.  Collect all shards on all ranks (before a
+        checkpoint, an evaluation through the fp32 parameters, or a switch of optimizer)."""
+        if self.px is None:
+            return
+        px = self.px
+        for r in range(px.world):
+            lo, hi = px.bounds[r], px.bounds[r + 1]
+            dist.broadcast(self.exp_avg[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+            dist.broadcast(self.exp_avg_sq[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+            for i, a, cnt in segment_pieces([(o, k) for _, o, k in self.segments], lo, hi):
+                p, off, _ = self.segments[i]
+                dist.broadcast(p.data.view(-1)[a - off:a - off + cnt], src=dist.get_global_rank(self.group, r) if self.group is not None else r,
+                               group=self.group)
 
     # ---- checkpoint interchange with the reference trainer (nerf/utils.py:1015-1136) --------------------------------
     # The reference builds torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15) with the groups
     # [encoder], [sigma_net], [encoder_dir] (no parameters), [color_net] (network_ff.py:137-149) and a torch.amp.GradScaler.
     def state_dict(self):
         """torch.optim.Adam-format state dict for the reference's parameter-group layout (loadable by its trainer)."""
+        self.gather_master()
         step = int(self.state[3].item())
         state = {}
         for i, (p, off, k) in enumerate(self.segments):
