@@ -294,7 +294,9 @@ def main():
         log(f"gradient exchange: {'peer memory (fused with the optimizer)' if fopt.px is not None else ('nccl all-reduce' if world > 1 else 'none (1 GPU)')}")
 
         from nerf_step import FusedTrainStep
-        ppoint = args.prefetch_point if args.prefetch_point != "auto" else ("exchange" if world > 1 else "start")
+        # where the next step's march is released: "start" (under this step's forward kernels, which leave registers / shared memory for
+        # its 64-thread blocks) measured faster than "exchange" at every N (8 GPUs, 200 steps: 1.145 vs 1.19 ms; profiles/r2_scale8_*.json)
+        ppoint = args.prefetch_point if args.prefetch_point != "auto" else "start"
         fstep = FusedTrainStep(model, fopt, R, perturb=True, chunks=args.chunks, prefetch_point=ppoint)
 
         def step(ro, rd, tgt):

@@ -117,7 +117,8 @@ int ngp_ffmlp_backward_ex(const void* grad, const void* inputs, const void* weig
                           uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
                           void* backward_buffer, void* grad_inputs, void* grad_weights,
                           void* workspace, size_t workspace_bytes, uint32_t flags, ngp_stream_t stream);
-/* zero_first != 0: clear the n_params-float workspace (start of a chunked pass); else convert it to fp16 grad_weights. */
+/* zero_first > 0: clear the n_params-float workspace (start of a chunked pass); 0: convert it to fp16 grad_weights; < 0: convert and
+ * leave the workspace cleared (a caller that keeps one persistent workspace then needs no memset per step). */
 int ngp_ffmlp_wgrad_finalize(void* workspace, void* grad_weights, uint32_t n_params, int zero_first,
                              ngp_stream_t stream);
 /* ffmlp.h:13-14 — the reference (re)creates global side streams here; this build needs none. */
@@ -272,6 +273,22 @@ int    ngp_exchange_adam(float* params, float* exp_avg_flat, float* exp_avg_sq_f
                          uint32_t world, uint64_t seg_off, uint64_t lo, uint64_t count, float lr, float beta1, float beta2,
                          float eps, const void* state, ngp_stream_t stream);
 int    ngp_exchange_zero(void* my_sink, uint64_t n, ngp_stream_t stream);
+/* Fused form of the same exchange (what the optimizer uses): the flag barriers ride inside the data kernels, three launches per step.
+ *   ngp_exchange_reduce_fused   signals "my bucket is complete", every CTA waits for all ranks, then reduces [lo, lo + count)
+ *   ngp_exchange_adam_fused     exchanges the non-finite flags, then Adam on the (<= 4) parameter pieces of the shard [shard_lo, shard_hi)
+ *                               (params_host[i] = fp32 master of the tensor whose element 0 has flat index seg_off_host[i]; piece =
+ *                               flat [lo_host[i], lo_host[i] + count_host[i])), stores the fp16 operand copies into every rank's shadow,
+ *                               clears the whole local bucket (n_total elements) and signals "my stores are done"
+ *   ngp_exchange_finish         waits for every rank's "done", then the GradScaler update (as ngp_optim_scaler_update) */
+int    ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, uint32_t rank, uint32_t world, uint64_t lo,
+                                 uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream);
+int    ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, uint32_t rank, uint32_t world,
+                               float* const* params_host, const uint64_t* seg_off_host, const uint64_t* lo_host,
+                               const uint64_t* count_host, uint32_t n_pieces, float* exp_avg_flat, float* exp_avg_sq_flat,
+                               void* my_sink, uint64_t shard_lo, uint64_t shard_hi, uint64_t n_total, float lr, float beta1,
+                               float beta2, float eps, void* state, uint32_t timeout_ms, ngp_stream_t stream);
+int    ngp_exchange_finish(void* const* pads_host, uint32_t rank, uint32_t world, void* state, float growth, float backoff,
+                           int growth_interval, uint32_t timeout_ms, ngp_stream_t stream);
 /* ---- occupancy-grid maintenance (replaces the Python/torch op sequences of
  * nerf/renderer.py:380-442 mark_untrained_grid and :445-538 update_extra_state).  density_grid is float [C, H^3] in Morton
  * order, bitfield uint8 [C*H^3/8] (the marcher's format, raymarching.cu:279-288).  All random numbers are caller-provided

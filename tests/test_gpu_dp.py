@@ -14,13 +14,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
-def test_two_rank_reduced_sink_equals_single_gpu_sink(tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_two_rank_reduced_sink_equals_single_gpu_sink(tmp_path, exchange):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from dp_sink_worker import sink_after_backward
     out = str(tmp_path / "sink2.pt")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29541", os.path.join(ROOT, "tests", "dp_sink_worker.py"), out],
+                        "--master-port", "29541" if exchange == "nccl" else "29547", os.path.join(ROOT, "tests", "dp_sink_worker.py"), out, exchange],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     two = torch.load(out)

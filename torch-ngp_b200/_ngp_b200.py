@@ -50,6 +50,10 @@ _SIGNATURES = {
     "ngp_exchange_reduce": [_vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _vp],
     "ngp_exchange_adam": [_vp, _vp, _vp, _vp, _vp, _u32, _c.c_uint64, _c.c_uint64, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp],
     "ngp_exchange_zero": [_vp, _c.c_uint64, _vp],
+    "ngp_exchange_reduce_fused": [_vp, _vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _u32, _vp],
+    "ngp_exchange_adam_fused": [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _c.c_uint64, _c.c_uint64, _c.c_uint64,
+                                _f32, _f32, _f32, _f32, _vp, _u32, _vp],
+    "ngp_exchange_finish": [_vp, _u32, _u32, _vp, _f32, _f32, _i32, _u32, _vp],
     "ngp_composite_rays_train_forward_mse": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "ngp_step_counter_push": [_vp, _vp, _vp, _vp, _vp],
     "ngp_density_grid_mark_untrained": [_vp, _u32, _f32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, _vp, _vp, _vp],

@@ -174,6 +174,187 @@ __global__ void __launch_bounds__(256) k_xchg_zero(uint4* __restrict__ sink, siz
         sink[i] = make_uint4(0, 0, 0, 0);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Fused form (what FusedFieldOptimizer uses): the three flag barriers ride inside the data kernels, so a step's exchange + optimizer
+// is THREE launches instead of eight —
+//   k_xchg_reduce_f : [signal "my bucket is complete" | every CTA waits for all ranks' signals] reduce my shard, inf/nan flag
+//   k_xchg_adam_f   : [signal found_inf | every CTA waits, ORs the flags] Adam on the pieces of my shard (or skip), shadows stored to
+//                     every replica, rest of my bucket cleared, [last CTA to finish signals "my shadow stores are done"]
+//   k_xchg_finish   : wait for every rank's "done", GradScaler update
+// Epochs live in the local pad (PAD_EPOCH + slot) and are advanced by the LAST CTA of the kernel that used them (ticket counter), so
+// all CTAs of a launch read the same value and a captured CUDA graph replays correctly.
+static constexpr uint32_t PAD_TICKET = 2560;      // per-kernel completion tickets
+
+__device__ __forceinline__ uint32_t wait_all_ranks(const uint32_t* my_pad_c, uint32_t* my_pad, uint32_t world, uint32_t slot, uint32_t epoch,
+                                                   unsigned long long timeout_ns) {
+    // executed by one full warp; returns the OR of the ranks' flag bits
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t bit = 0;
+    if (lane < world) {
+        const uint32_t* src = my_pad_c + slot * PAD_SLOT_STRIDE + lane;
+        const unsigned long long t0 = globaltimer_ns();
+        uint32_t v = ld_acquire_sys(src);
+        while ((v >> 1) < epoch) {
+            if (*reinterpret_cast<volatile uint32_t*>(my_pad + PAD_ERROR) != 0u) break;
+            if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(my_pad + PAD_ERROR, 1u + slot); break; }
+            __nanosleep(32);
+            v = ld_acquire_sys(src);
+        }
+        bit = v & 1u;
+    }
+    return __any_sync(0xffffffffu, bit != 0u) ? 1u : 0u;
+}
+__device__ __forceinline__ void signal_all_ranks(const PeerPtrs& pads, uint32_t rank, uint32_t world, uint32_t slot, uint32_t value) {
+    const uint32_t lane = threadIdx.x & 31u;
+    __threadfence_system();
+    if (lane < world) st_release_sys(reinterpret_cast<uint32_t*>(pads.p[lane]) + slot * PAD_SLOT_STRIDE + rank, value);
+}
+// last CTA of the launch (all others have passed their fence + ticket): returns true in exactly one CTA, for all its threads
+__device__ __forceinline__ bool last_cta_done(uint32_t* ticket) {
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1u) ? 1u : 0u;
+        if (s_last) { *ticket = 0u; __threadfence_system(); }
+    }
+    __syncthreads();
+    return s_last != 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_xchg_reduce_f(PeerPtrs pads, PeerPtrs sinks, uint32_t rank, uint32_t world, size_t lo8, size_t n8, ScalerStateX* __restrict__ st,
+                unsigned long long timeout_ns) {
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(pads.p[rank]);
+    const uint32_t epoch = my_pad[PAD_EPOCH + 0] + 1u;
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0) signal_all_ranks(pads, rank, world, 0, epoch << 1);
+        wait_all_ranks(my_pad, my_pad, world, 0, epoch, timeout_ns);
+    }
+    __syncthreads();
+    uint4* my_sink = reinterpret_cast<uint4*>(sinks.p[rank]);
+    bool bad = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 v[MAX_WORLD];
+#pragma unroll
+        for (uint32_t p = 0; p < MAX_WORLD; ++p)
+            if (p < world) v[p] = reinterpret_cast<const uint4*>(sinks.p[p])[lo8 + i];
+#pragma unroll
+        for (uint32_t p = 0; p < MAX_WORLD; ++p) {
+            if (p < world) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[p]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(h[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+            }
+        }
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+            ow[k] = *reinterpret_cast<const uint32_t*>(&h);
+            bad |= half2_nonfinite(ow[k]);
+        }
+        my_sink[lo8 + i] = o;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31u) == 0) atomicOr(&st->found_inf, 1);
+    if (last_cta_done(my_pad + PAD_TICKET + 0) && threadIdx.x == 0) my_pad[PAD_EPOCH + 0] = epoch;
+}
+
+struct AdamPieces {            // the pieces of this rank's shard, one per parameter tensor it intersects
+    float* p[4];
+    unsigned long long seg_off[4], lo8[4], n8[4];
+    uint32_t count;
+};
+
+__global__ void __launch_bounds__(256)
+k_xchg_adam_f(PeerPtrs pads, PeerPtrs shadows, uint32_t rank, uint32_t world, AdamPieces pieces, float* __restrict__ m, float* __restrict__ v,
+              uint4* __restrict__ sink, size_t shard_lo8, size_t shard_hi8, size_t total8, float lr, float beta1, float beta2, float eps,
+              ScalerStateX* __restrict__ st, unsigned long long timeout_ns) {
+    __shared__ uint32_t s_skip;
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(pads.p[rank]);
+    const uint32_t e1 = my_pad[PAD_EPOCH + 1] + 1u;
+    if (threadIdx.x < 32) {
+        // the reduce kernel has completed (stream order): this rank's non-finite flag is final
+        if (blockIdx.x == 0) signal_all_ranks(pads, rank, world, 1, (e1 << 1) | (st->found_inf != 0 ? 1u : 0u));
+        const uint32_t any = wait_all_ranks(my_pad, my_pad, world, 1, e1, timeout_ns);
+        if (threadIdx.x == 0) {
+            s_skip = any;
+            if (any && blockIdx.x == 0) st->found_inf = 1;          // for the scaler update (only this CTA touches it here)
+        }
+    }
+    __syncthreads();
+    const bool skip = s_skip != 0u;
+    const float inv_scale = 1.0f / st->scale;
+    const int step = st->step + 1;
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    const float step_size = lr * st->lr_scale / bc1;
+    const float rsqrt_bc2 = rsqrtf(bc2);
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (size_t)gridDim.x * blockDim.x;
+    for (uint32_t pc = 0; pc < pieces.count; ++pc) {
+        float* __restrict__ p = pieces.p[pc];
+        const size_t seg_off = pieces.seg_off[pc], lo8 = pieces.lo8[pc], n8 = pieces.n8[pc];
+        for (size_t i = gtid; i < n8; i += gstride) {
+            const size_t f8 = lo8 + i;
+            const uint4 gr = sink[f8];
+            sink[f8] = make_uint4(0, 0, 0, 0);               // this element of the bucket is consumed
+            if (skip) continue;
+            const __half2* gh = reinterpret_cast<const __half2*>(&gr);
+            float4* pp = reinterpret_cast<float4*>(p + (f8 * 8 - seg_off));
+            float4* mp = reinterpret_cast<float4*>(m + f8 * 8);
+            float4* vp = reinterpret_cast<float4*>(v + f8 * 8);
+            uint4 sh;
+            uint32_t* shw = reinterpret_cast<uint32_t*>(&sh);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float4 P = pp[q], Mm = mp[q], V = vp[q];
+                float* pf = reinterpret_cast<float*>(&P); float* mf = reinterpret_cast<float*>(&Mm); float* vf = reinterpret_cast<float*>(&V);
+                const float2 g01 = __half22float2(gh[2 * q]), g23 = __half22float2(gh[2 * q + 1]);
+                const float gi[4] = {g01.x * inv_scale, g01.y * inv_scale, g23.x * inv_scale, g23.y * inv_scale};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mf[k] = fmaf(beta1, mf[k], omb1 * gi[k]);
+                    vf[k] = fmaf(beta2, vf[k], omb2 * gi[k] * gi[k]);
+                    pf[k] = pf[k] - step_size * (mf[k] / (sqrtf(vf[k]) * rsqrt_bc2 + eps));
+                }
+                pp[q] = P; mp[q] = Mm; vp[q] = V;
+                const __half2 s01 = __floats2half2_rn(pf[0], pf[1]), s23 = __floats2half2_rn(pf[2], pf[3]);
+                shw[2 * q] = *reinterpret_cast<const uint32_t*>(&s01);
+                shw[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&s23);
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < MAX_WORLD; ++q)
+                if (q < world) reinterpret_cast<uint4*>(shadows.p[q])[f8] = sh;
+        }
+    }
+    // the other ranks' shards of my bucket: everybody has read them (barrier 1), clear them for the next step
+    for (size_t i = gtid; i < total8; i += gstride)
+        if (i < shard_lo8 || i >= shard_hi8) sink[i] = make_uint4(0, 0, 0, 0);
+    // my stores into the replicas' shadows are complete once every CTA of this launch is past this point
+    if (last_cta_done(my_pad + PAD_TICKET + 1)) {
+        const uint32_t e2 = my_pad[PAD_EPOCH + 2] + 1u;
+        if (threadIdx.x < 32) signal_all_ranks(pads, rank, world, 2, e2 << 1);
+        if (threadIdx.x == 0) { my_pad[PAD_EPOCH + 1] = e1; my_pad[PAD_EPOCH + 2] = e2; }
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_xchg_finish(PeerPtrs pads, uint32_t rank, uint32_t world, ScalerStateX* __restrict__ st, float growth, float backoff, int growth_interval,
+              unsigned long long timeout_ns) {
+    uint32_t* my_pad = reinterpret_cast<uint32_t*>(pads.p[rank]);
+    const uint32_t e2 = my_pad[PAD_EPOCH + 2];         // advanced by k_xchg_adam_f of this step
+    wait_all_ranks(my_pad, my_pad, world, 2, e2, timeout_ns);
+    if (threadIdx.x == 0) {                              // GradScaler.update() (same rule as k_scaler_update)
+        if (st->found_inf) { st->scale *= backoff; st->growth_tracker = 0; }
+        else { st->step += 1; if (++st->growth_tracker >= growth_interval) { st->scale *= growth; st->growth_tracker = 0; } }
+        st->found_inf = 0;
+    }
+}
+
 static uint32_t grid_for(size_t n, uint32_t per_sm) {
     const size_t blocks = (n + 255) / 256;
     const size_t cap = (size_t)sm_count() * per_sm;
@@ -291,4 +472,61 @@ extern "C" int ngp_exchange_zero(void* my_sink, uint64_t n, ngp_stream_t stream)
     if (n == 0) return NGP_OK;
     k_xchg_zero<<<grid_for(n / 8, 8), 256, 0, as_stream(stream)>>>((uint4*)my_sink, n / 8);
     return check_launch("exchange_zero");
+}
+
+// ---- fused form: three launches per step (see the kernels' comment) ----
+extern "C" int ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, uint32_t rank, uint32_t world, uint64_t lo,
+                                         uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream) {
+    PeerPtrs pp, sp;
+    int rc = fill_ptrs(pp, pads_host, world, "exchange_reduce_fused");
+    if (rc) return rc;
+    rc = fill_ptrs(sp, sinks_host, world, "exchange_reduce_fused");
+    if (rc) return rc;
+    if (rank >= world || (lo & 7) || (count & 7) || !state) return fail(NGP_EINVAL, "exchange_reduce_fused: bad arguments");
+    // every CTA spins on the ranks' flags before it reduces: the grid must be co-resident (<= 8 CTAs of 256 threads per SM)
+    k_xchg_reduce_f<<<grid_for(count / 8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sp, rank, world, lo / 8, count / 8, (ScalerStateX*)state,
+                                                                             (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull);
+    return check_launch("exchange_reduce_fused");
+}
+
+// params_host / seg_off_host / lo_host / count_host: n_pieces (<= 4) parameter pieces of this rank's shard [shard_lo, shard_hi);
+// n_total = size of the flat bucket.  Also clears the bucket and signals completion of the shadow stores.
+extern "C" int ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, uint32_t rank, uint32_t world,
+                                       float* const* params_host, const uint64_t* seg_off_host, const uint64_t* lo_host,
+                                       const uint64_t* count_host, uint32_t n_pieces, float* exp_avg_flat, float* exp_avg_sq_flat,
+                                       void* my_sink, uint64_t shard_lo, uint64_t shard_hi, uint64_t n_total, float lr, float beta1,
+                                       float beta2, float eps, void* state, uint32_t timeout_ms, ngp_stream_t stream) {
+    PeerPtrs pp, sh;
+    int rc = fill_ptrs(pp, pads_host, world, "exchange_adam_fused");
+    if (rc) return rc;
+    rc = fill_ptrs(sh, shadows_host, world, "exchange_adam_fused");
+    if (rc) return rc;
+    if (rank >= world || n_pieces > 4 || !exp_avg_flat || !exp_avg_sq_flat || !my_sink || !state || ((shard_lo | shard_hi | n_total) & 7))
+        return fail(NGP_EINVAL, "exchange_adam_fused: bad arguments");
+    AdamPieces pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.count = n_pieces;
+    size_t work8 = 0;
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        if (!params_host[i] || ((seg_off_host[i] | lo_host[i] | count_host[i]) & 7) || lo_host[i] < seg_off_host[i])
+            return fail(NGP_EINVAL, "exchange_adam_fused: bad piece %u", i);
+        pc.p[i] = params_host[i]; pc.seg_off[i] = seg_off_host[i]; pc.lo8[i] = lo_host[i] / 8; pc.n8[i] = count_host[i] / 8;
+        work8 += count_host[i] / 8;
+    }
+    k_xchg_adam_f<<<grid_for(work8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sh, rank, world, pc, exp_avg_flat, exp_avg_sq_flat, (uint4*)my_sink,
+                                                                        shard_lo / 8, shard_hi / 8, n_total / 8, lr, beta1, beta2, eps,
+                                                                        (ScalerStateX*)state,
+                                                                        (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull);
+    return check_launch("exchange_adam_fused");
+}
+
+extern "C" int ngp_exchange_finish(void* const* pads_host, uint32_t rank, uint32_t world, void* state, float growth, float backoff,
+                                   int growth_interval, uint32_t timeout_ms, ngp_stream_t stream) {
+    PeerPtrs pp;
+    int rc = fill_ptrs(pp, pads_host, world, "exchange_finish");
+    if (rc) return rc;
+    if (rank >= world || !state) return fail(NGP_EINVAL, "exchange_finish: bad arguments");
+    k_xchg_finish<<<1, 32, 0, as_stream(stream)>>>(pp, rank, world, (ScalerStateX*)state, growth, backoff, growth_interval,
+                                                  (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull);
+    return check_launch("exchange_finish");
 }

@@ -33,6 +33,14 @@
 namespace ngp {
 using namespace umma;
 
+// four adjacent fp32 sums in one 16-byte L2 reduction (the weight-gradient flush: every CTA / tile context adds its [64 x 64] fp32
+// accumulators into the same 72 KB workspace — at small batches per rank that flush is a visible share of the kernel, and one v4
+// reduction replaces four scalar atomics on the same 32-byte sector).  dst must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4_f32(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+                 "f"(__uint_as_float(c)), "f"(__uint_as_float(d)) : "memory");
+}
+
 // ---- fused field front/back ends -----------------------------------------------------------------
 // The MLP kernels can be fed / drained on chip instead of through HBM tensors:
 //   IN_GRID : the input tile is produced by the hash-grid encoder in the kernel itself (thread = sample, 16 levels
@@ -57,6 +65,7 @@ struct FieldArgs {
     uint32_t gridtype;
     int align_corners;
     __half* feat_out;        // [M, 2L] stash (nullable)
+    int pair_loads;          // IN_GRID gathers: 8-byte loads of aligned x-pairs (see write_grid_row)
     // IN_SHGEO (and the color backward)
     const float* dirs;       // [M,3]
     const __half* h_sigma;   // [M,16]
@@ -167,8 +176,26 @@ __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, b
                 uint32_t cidx[8];
                 corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
                 const uint32_t* lvl = reinterpret_cast<const uint32_t*>(fa.table) + P.off;
+                if (fa.pair_loads && (P.off & 1u) == 0u) {
+                    // corners 2j / 2j+1 differ only in x.  ONE 8-byte load of the aligned entry pair that holds corner 2j also
+                    // delivers corner 2j+1 whenever the two entries are that pair (dense level with an even index, hashed level
+                    // with an even x: half of all cases); only otherwise a second 4-byte load is issued (predicated, never a third
+                    // one).  The kernel is bound by L1 wavefronts (ncu r2: l1tex 69 %, every 4-byte corner load of a fine level is
+                    // a wavefront of its own): this removes a quarter of them.  Same values, same blend order.
 #pragma unroll
-                for (uint32_t i = 0; i < 8; ++i) vals[q][i] = __ldg(lvl + cidx[i]);
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(lvl + (i0 & ~1u)));
+                        const bool hi0 = (i0 & 1u) != 0u;
+                        vals[q][2 * j] = hi0 ? a.y : a.x;
+                        uint32_t b = hi0 ? a.x : a.y;
+                        if ((i0 ^ i1) != 1u) b = __ldg(lvl + i1);
+                        vals[q][2 * j + 1] = b;
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t i = 0; i < 8; ++i) vals[q][i] = __ldg(lvl + cidx[i]);
+                }
             }
             // phase 2: blend in the reference's corner order
 #pragma unroll
@@ -819,9 +846,9 @@ k_ffmlp_backward_fused(const __half* __restrict__ grad, const __half* __restrict
                 if (l < nmat && m < Mv) {
                     float* dst = wgrad_ws + ws_off + (size_t)m * Nv;
 #pragma unroll
-                    for (uint32_t i = 0; i < 32; ++i) {
+                    for (uint32_t i = 0; i < 32; i += 4) {
                         const uint32_t n = half_i * 32 + i;
-                        if (n < Nv) atomicAdd(dst + n, __uint_as_float(v[i]));
+                        if (n < Nv) red_add_v4_f32(dst + n, v[i], v[i + 1], v[i + 2], v[i + 3]);
                     }
                 }
             }
@@ -1157,9 +1184,9 @@ k_ffmlp_backward_dual(const __half* __restrict__ grad, const __half* __restrict_
                     if (l < nmat && m < Mv) {
                         float* dst = wgrad_ws + ws_off + (size_t)m * Nv;
 #pragma unroll
-                        for (uint32_t i = 0; i < 32; ++i) {
+                        for (uint32_t i = 0; i < 32; i += 4) {
                             const uint32_t n = half_i * 32 + i;
-                            if (n < Nv) atomicAdd(dst + n, __uint_as_float(v[i]));
+                            if (n < Nv) red_add_v4_f32(dst + n, v[i], v[i + 1], v[i + 2], v[i + 3]);
                         }
                     }
                 }
@@ -1283,6 +1310,11 @@ k_ffmlp_wgrad(const __half* __restrict__ grad, const __half* __restrict__ inputs
 __global__ void k_ffmlp_wgrad_finalize(const float* __restrict__ ws, __half* __restrict__ grad_weights, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) grad_weights[i] = __float2half_rn(ws[i]);
+}
+// convert and leave the workspace cleared for the next accumulation pass (callers that keep one persistent workspace)
+__global__ void k_ffmlp_wgrad_finalize_clear(float* __restrict__ ws, __half* __restrict__ grad_weights, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { grad_weights[i] = __float2half_rn(ws[i]); ws[i] = 0.f; }
 }
 
 // ================================ debug probe (tests only) =====================================
@@ -1520,12 +1552,15 @@ extern "C" int ngp_ffmlp_backward(const void* grad, const void* inputs, const vo
 extern "C" int ngp_ffmlp_wgrad_finalize(void* workspace, void* grad_weights, uint32_t n_params, int zero_first, ngp_stream_t stream) {
     if (!workspace) return fail(NGP_EINVAL, "ffmlp_wgrad_finalize: workspace is null");
     cudaStream_t st = as_stream(stream);
-    if (zero_first) {
+    if (zero_first > 0) {
         if (cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)n_params, st) != cudaSuccess) return fail(NGP_ECUDA, "ffmlp_wgrad_finalize: memset failed");
         return NGP_OK;
     }
     if (!grad_weights) return fail(NGP_EINVAL, "ffmlp_wgrad_finalize: grad_weights is null");
-    k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
+    if (zero_first < 0)     // convert, then clear: the workspace is ready for the next accumulation pass without a memset
+        k_ffmlp_wgrad_finalize_clear<<<div_up(n_params, 256u), 256, 0, st>>>((float*)workspace, (__half*)grad_weights, n_params);
+    else
+        k_ffmlp_wgrad_finalize<<<div_up(n_params, 256u), 256, 0, st>>>((const float*)workspace, (__half*)grad_weights, n_params);
     return check_launch("ffmlp_wgrad_finalize");
 }
 
@@ -1551,6 +1586,8 @@ static int field_sigma_forward_impl(const float* x01, float bound, const uint32_
     fa.xyz = x01; fa.bound = bound; fa.inv_2bound = bound > 0.f ? 1.0f / (2.0f * bound) : 1.f; fa.rows_dev = rows_dev; fa.table = (const __half*)table_f16; fa.offsets = offsets; fa.L = L;
     fa.S = S; fa.H = H; fa.gridtype = gridtype; fa.align_corners = align_corners; fa.feat_out = (__half*)feat_out;
     fa.sigma_out = sigma_out;
+    static const int pair_env = [] { const char* e = getenv("NGP_SIGMA_PAIR_LOADS"); return (e && e[0] == '1') ? 1 : 0; }();
+    fa.pair_loads = pair_env && (reinterpret_cast<uintptr_t>(table_f16) & 7u) == 0;
     const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
     // The kernel is bound by its table gathers (128 per sample), i.e. by L1 hit rate and L2->L1 sector traffic.  Shared memory and
     // L1 share 256 KB per SM: at the occupancy the registers allow (5 CTAs x 42 KB) the driver carves 228 KB for shared memory and

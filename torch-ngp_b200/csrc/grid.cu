@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(512, (D <= 3 && C <= 2) ? 3 : 1)     // NeRF /
 k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 const int* __restrict__ offsets, T* __restrict__ grad_table, const uint32_t B,
                 const uint32_t L, const float S, const uint32_t H, const uint32_t gridtype,
-                const bool align_corners, const uint32_t interp, const bool level_major, const bool staged) {
+                const bool align_corners, const uint32_t interp, const bool level_major, const bool staged, const uint32_t merge_min) {
     extern __shared__ __align__(16) uint32_t stage_sm[];
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x;
@@ -315,40 +315,59 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
     const uint32_t F = L * C;
     const uint32_t ntiles = div_up(B, TILE_PTS);
     constexpr uint32_t EW = (C * (uint32_t)sizeof(T)) / 4;            // 32-bit words per (level, point) gradient entry (staged form)
+    // A CTA iteration handles a GROUP of two consecutive 32-point tiles: warp w works on level w of the first tile and on level
+    // L-1-w of the second, so that every warp gets one cheap and one expensive level per iteration (coarse levels pay for deep run
+    // scans, fine levels for many reductions: with one tile per iteration a quarter of the stall samples sat at the CTA barrier,
+    // ncu r2b) and the staging barrier is crossed once per 64 points.
+    constexpr uint32_t GROUP = 2;
+    const uint32_t ngroups = div_up(ntiles, GROUP);
     const uint32_t row_words = (F * (uint32_t)sizeof(T)) / 4;
     const uint32_t pitch = row_words | 1u;
-    const uint32_t buf_words = TILE_PTS * pitch + TILE_PTS * D;
-    auto issue = [&](uint32_t tile, uint32_t buf) {
-        if (tile < ntiles) {
-            uint32_t* sg = stage_sm + buf * buf_words;
-            float* sx = reinterpret_cast<float*>(sg + TILE_PTS * pitch);
-            const uint32_t b0 = tile * TILE_PTS;
-            const uint32_t npts = min(TILE_PTS, B - b0);
+    const uint32_t tile_words = TILE_PTS * pitch + TILE_PTS * D;
+    const uint32_t buf_words = GROUP * tile_words;
+    auto issue = [&](uint32_t group, uint32_t buf) {
+        if (group < ngroups) {
+            const uint32_t b0 = group * GROUP * TILE_PTS;
+            const uint32_t npts = min(GROUP * TILE_PTS, B - b0);
             const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(grad + (size_t)b0 * F);
             for (uint32_t i = tid; i < npts * row_words; i += nthr) {
                 const uint32_t r = i / row_words, w = i - r * row_words;
-                cp_async_4(sg + r * pitch + w, gsrc + i);
+                uint32_t* sg = stage_sm + buf * buf_words + (r / TILE_PTS) * tile_words;
+                cp_async_4(sg + (r % TILE_PTS) * pitch + w, gsrc + i);
             }
             const float* xsrc = inputs + (size_t)b0 * D;
-            for (uint32_t i = tid; i < npts * D; i += nthr) cp_async_4(sx + i, xsrc + i);
+            for (uint32_t i = tid; i < npts * D; i += nthr) {
+                const uint32_t r = i / D;
+                float* sx = reinterpret_cast<float*>(stage_sm + buf * buf_words + (r / TILE_PTS) * tile_words + TILE_PTS * pitch);
+                cp_async_4(sx + (i - (r / TILE_PTS) * TILE_PTS * D), xsrc + i);
+            }
         }
         cp_async_commit_group();          // one group per call, also when empty: the wait distance below stays fixed
     };
     if (staged) issue(blockIdx.x, 0);
-    const bool fixed_level = L <= nwarp;
-    const BwdLevel P_fixed = make_bwd_level<D>(offsets, warp < L ? warp : 0u, S, H, gridtype, align_corners);
+    // per-level constants: computed once per CTA, read back from shared memory per (tile, level)
+    constexpr uint32_t MAX_TAB = 64;
+    __shared__ BwdLevel s_levels[MAX_TAB];
+    const bool tabled = L <= MAX_TAB;
+    if (tabled && tid < L) s_levels[tid] = make_bwd_level<D>(offsets, tid, S, H, gridtype, align_corners);
+    __syncthreads();
+    const bool mirror = L == nwarp;        // second tile of a group: warp w takes level L-1-w
 
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t b = tile * TILE_PTS + lane;
-        bool active = b < B;
-        const uint32_t* sg = stage_sm + (it & 1u) * buf_words;
-        const float* sx = reinterpret_cast<const float*>(sg + TILE_PTS * pitch);
+    for (uint32_t group = blockIdx.x; group < ngroups; group += gridDim.x, ++it) {
         if (staged) {
-            issue(tile + gridDim.x, (it + 1u) & 1u);
+            issue(group + gridDim.x, (it + 1u) & 1u);
             cp_async_wait_group<1>();
             __syncthreads();
         }
+#pragma unroll 1
+      for (uint32_t half = 0; half < GROUP; ++half) {
+        const uint32_t tile = group * GROUP + half;
+        const uint32_t b = tile * TILE_PTS + lane;
+        bool active = b < B;
+        const uint32_t* sg = stage_sm + (it & 1u) * buf_words + half * tile_words;
+        const float* sx = reinterpret_cast<const float*>(sg + TILE_PTS * pitch);
+        const bool flip = mirror && half == 1u;
 
         float x[D];
 #pragma unroll
@@ -363,8 +382,9 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
             for (uint32_t d = 0; d < D; ++d) x[d] = 0.5f;
         }
 
-        for (uint32_t level = warp; any_active && level < L; level += nwarp) {
-            const BwdLevel P = fixed_level ? P_fixed : make_bwd_level<D>(offsets, level, S, H, gridtype, align_corners);
+        for (uint32_t lv = warp; any_active && lv < L; lv += nwarp) {
+            const uint32_t level = flip ? L - 1u - lv : lv;
+            const BwdLevel P = tabled ? s_levels[level] : make_bwd_level<D>(offsets, level, S, H, gridtype, align_corners);
             const uint32_t off = P.off;
             const float scale = P.scale;
             T* __restrict__ lvl = grad_table + (size_t)off * C;
@@ -414,8 +434,12 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
             const bool head = (lane == 0) || !same;
             const uint32_t heads = __ballot_sync(FULL, head);
             const uint32_t my_head = 31u - __clz(heads & (FULL >> (31u - lane)));
-            const uint32_t maxrun = __reduce_max_sync(FULL, lane - my_head) + 1u;      // redux.sync: longest run in the warp
-            const bool issue_red = active && ((lane == 31u) || ((heads >> (lane + 1u)) & 1u));
+            // Merging costs issue slots (4 shuffles + 4 predicated adds per corner pair and scan step) and saves reduction lane-ops
+            // (LSU / L2).  The kernel is issue-bound (ncu r2: 74 % issue-slot utilisation, reductions at 54 % of the measured L2
+            // reduction rate), so runs are merged only where enough lanes fold away to pay for the scan (warp-uniform decision).
+            const bool do_merge = (32u - __popc(heads)) >= merge_min;
+            const uint32_t maxrun = do_merge ? __reduce_max_sync(FULL, lane - my_head) + 1u : 1u;      // redux.sync: longest run in the warp
+            const bool issue_red = active && (!do_merge || (lane == 31u) || ((heads >> (lane + 1u)) & 1u));
 
             if constexpr (C == 2) {
                 // corners 2j and 2j+1 differ only in x.  When their entries are an aligned adjacent pair (dense level with an
@@ -507,6 +531,7 @@ k_grid_backward(const T* __restrict__ grad, const float* __restrict__ inputs,
                 }
             }
         }
+      }
         if (staged) __syncthreads();       // everybody is done with this buffer before the next iteration's copy lands in it
     }
 }
@@ -650,16 +675,18 @@ static int launch_bwd(const void* grad, const float* inputs, const int* offsets,
                       bool ac, uint32_t interp, bool level_major, cudaStream_t st) {
     const uint32_t nw = L < 16 ? L : 16;
     dim3 block(32, nw);
-    const uint32_t ntiles = div_up(B, TILE_PTS);
+    const uint32_t ngroups = div_up(div_up(B, TILE_PTS), 2u);              // a CTA iteration handles two 32-point tiles
     const uint32_t cap = (uint32_t)sm_count() * (nw > 8 ? 3u : 6u);      // resident CTAs per SM at 40 registers / thread
-    dim3 grid(ntiles < cap ? ntiles : cap);
+    dim3 grid(ngroups < cap ? ngroups : cap);
     // staged (cp.async double-buffered) inputs: point-major gradients whose (level, point) entries are whole 32-bit words
     const uint32_t row_words = (uint32_t)(((size_t)L * C * sizeof(T)) / 4);
-    const size_t smem = 2 * (size_t)(TILE_PTS * (row_words | 1u) + TILE_PTS * D) * 4;
-    static const bool stage_env = [] { const char* e = getenv("NGP_GRID_BWD_STAGED"); return !(e && e[0] == '0'); }();
+    const size_t smem = 2 * 2 * (size_t)(TILE_PTS * (row_words | 1u) + TILE_PTS * D) * 4;      // 2 buffers x 2 tiles
+    static const bool stage_env = [] { const char* e = getenv("NGP_GRID_BWD_STAGED"); return e && e[0] == '1'; }();
+    // runs of equal cells are merged by a warp scan only when at least this many of the 32 lanes would fold away (see the kernel)
+    static const uint32_t merge_min = [] { const char* e = getenv("NGP_GRID_MERGE_MIN"); return e ? (uint32_t)atoi(e) : 0u; }();
     const bool staged = stage_env && !level_major && (C * sizeof(T)) % 4 == 0 && smem <= 40 * 1024;
     k_grid_backward<T, D, C><<<grid, block, staged ? smem : 0, st>>>((const T*)grad, inputs, offsets, (T*)gemb, B, L, S, H,
-                                                                      gridtype, ac, interp, level_major, staged);
+                                                                      gridtype, ac, interp, level_major, staged, merge_min);
     int rc = check_launch("grid_encode_backward");
     if (rc) return rc;
     if (dy_dx && ginp) {

@@ -84,6 +84,17 @@ def field_forward(xyzs, dirs, embeddings, offsets, sigma_w, color_w, cfg, chunks
     return sigma, rgb, stash
 
 
+_WGRAD_WS = {}
+
+
+def _wgrad_workspace(dev, n):
+    key = (str(dev), int(n))
+    w = _WGRAD_WS.get(key)
+    if w is None:
+        w = _WGRAD_WS[key] = torch.zeros(n, dtype=torch.float32, device=dev)
+    return w
+
+
 def field_backward(tensors, cfg, sinks, d_sigma, d_rgb, side=None):
     """Raw backward of field_forward: returns (g_table, gw_sigma, gw_color) — the sinks themselves when installed.
     With a side stream and more than one chunk the table scatter of chunk k runs under the MLP backward kernels of chunk k+1."""
@@ -102,16 +113,16 @@ def field_backward(tensors, cfg, sinks, d_sigma, d_rgb, side=None):
     g_table = sink_t if sink_t is not None else torch.zeros(table_shape, dtype=torch.half, device=dev)
     nb_c = lib.ngp_ffmlp_backward_workspace_bytes(M, 32, 16, 64, nl_c)
     nb_s = lib.ngp_ffmlp_backward_workspace_bytes(M, 2 * L, 16, 64, nl_s)
-    wk_c = torch.empty(nb_c // 4, dtype=torch.float32, device=dev)
-    wk_s = torch.empty(nb_s // 4, dtype=torch.float32, device=dev)
+    # one persistent fp32 workspace [sigma | color] (the order of the weights in the optimizer's flat bucket), zero on creation and
+    # cleared again by every finalize: no memset per step
+    wk = _wgrad_workspace(dev, (nb_s + nb_c) // 4)
+    wk_s, wk_c = wk[:nb_s // 4], wk[nb_s // 4:]
     dys = torch.empty(M, 16, dtype=torch.half, device=dev)          # dL/d(sigma-net output)
     d_feat = torch.empty(M, 2 * L, dtype=torch.half, device=dev)    # dL/d(encoder features)
     main = torch.cuda.current_stream()
     piped = side is not None and nck > 1
     if piped:
         side.wait_stream(main)
-    _backend.call("ngp_ffmlp_wgrad_finalize", wk_c.data_ptr(), None, nb_c // 4, 1)
-    _backend.call("ngp_ffmlp_wgrad_finalize", wk_s.data_ptr(), None, nb_s // 4, 1)
     flags = WGRAD_ACCUMULATE | WGRAD_NO_FINALIZE
     for k, (r0, rows) in enumerate(ranges):
         # color net (+ sigmoid, cat, trunc_exp gradients) -> dL/d(sigma-net output)
@@ -129,8 +140,11 @@ def field_backward(tensors, cfg, sinks, d_sigma, d_rgb, side=None):
         with torch.cuda.stream(side if piped else main):
             _backend.call("ngp_grid_encode_backward", d_feat.data_ptr() + 4 * L * r0, x01.data_ptr() + 12 * r0, None, offsets.data_ptr(),
                           g_table.data_ptr(), rows, 3, 2, L, S, H, None, None, gridtype, align_corners, 0, 1, 0)
-    _backend.call("ngp_ffmlp_wgrad_finalize", wk_c.data_ptr(), gw_c.data_ptr(), nb_c // 4, 0)
-    _backend.call("ngp_ffmlp_wgrad_finalize", wk_s.data_ptr(), gw_s.data_ptr(), nb_s // 4, 0)
+    if gw_c.data_ptr() == gw_s.data_ptr() + nb_s // 2:       # adjacent in the flat bucket: one launch converts both
+        _backend.call("ngp_ffmlp_wgrad_finalize", wk.data_ptr(), gw_s.data_ptr(), (nb_s + nb_c) // 4, -1)
+    else:
+        _backend.call("ngp_ffmlp_wgrad_finalize", wk_s.data_ptr(), gw_s.data_ptr(), nb_s // 4, -1)
+        _backend.call("ngp_ffmlp_wgrad_finalize", wk_c.data_ptr(), gw_c.data_ptr(), nb_c // 4, -1)
     if piped:
         main.wait_stream(side)
     return g_table, gw_s, gw_c

@@ -61,6 +61,7 @@ class FusedFieldOptimizer:
         self.state[0:1].view(torch.float32).fill_(init_scale)
         self.state[4:5].view(torch.float32).fill_(1.0)
         self._exchange = None
+        self._fused_args = None
         self.segments = []
         off = 0
         for p in self.params:
@@ -146,21 +147,27 @@ class FusedFieldOptimizer:
                       int(self.growth_interval))
 
     def _apply_peer(self):
+        """Three launches (csrc/exchange.cu, fused form): [all buckets complete | reduce my shard] -> [non-finite flags OR-ed over the ranks |
+        Adam on my shard, operand copies into every replica, bucket cleared | "my stores are done"] -> [all replicas complete | scaler]."""
         px = self.px
         lo, hi = px.my_range
-        found = self.state.data_ptr() + 8          # &state.found_inf
-        px.barrier(0)
-        _backend.call("ngp_exchange_reduce", px.sinks, px.rank, px.world, lo, hi - lo, self.state.data_ptr())
-        px.barrier(1, found, found)
-        for i, a, cnt in self._pieces:
-            p, off, _ = self.segments[i]
-            _backend.call("ngp_exchange_adam", p.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.sink.data_ptr(),
-                          px.shadows, px.world, off, a, cnt, float(self.lr), float(self.betas[0]), float(self.betas[1]),
-                          float(self.eps), self.state.data_ptr())
-        _backend.call("ngp_exchange_zero", self.sink.data_ptr(), self.sink.numel())
-        px.barrier(2)
-        _backend.call("ngp_optim_scaler_update", self.state.data_ptr(), float(self.growth), float(self.backoff),
-                      int(self.growth_interval))
+        if self._fused_args is None:
+            import ctypes
+            n = len(self._pieces)
+            P = (ctypes.c_void_p * 4)(*[self.segments[i][0].data_ptr() for i, _, _ in self._pieces] + [None] * (4 - n))
+            U = ctypes.c_uint64 * 4
+            seg = U(*[self.segments[i][1] for i, _, _ in self._pieces] + [0] * (4 - n))
+            los = U(*[a for _, a, _ in self._pieces] + [0] * (4 - n))
+            cnt = U(*[c for _, _, c in self._pieces] + [0] * (4 - n))
+            self._fused_args = (P, seg, los, cnt, n)
+        P, seg, los, cnt, n = self._fused_args
+        tmo = 20000
+        _backend.call("ngp_exchange_reduce_fused", px.pads, px.sinks, px.rank, px.world, lo, hi - lo, self.state.data_ptr(), tmo)
+        _backend.call("ngp_exchange_adam_fused", px.pads, px.shadows, px.rank, px.world, P, seg, los, cnt, n, self.exp_avg.data_ptr(),
+                      self.exp_avg_sq.data_ptr(), self.sink.data_ptr(), lo, hi, self.sink.numel(), float(self.lr), float(self.betas[0]),
+                      float(self.betas[1]), float(self.eps), self.state.data_ptr(), tmo)
+        _backend.call("ngp_exchange_finish", px.pads, px.rank, px.world, self.state.data_ptr(), float(self.growth), float(self.backoff),
+                      int(self.growth_interval), tmo)
 
     @torch.no_grad()
     def gather_master(self):
