@@ -291,7 +291,8 @@ def main():
         from ngp_optim import FusedFieldOptimizer
         fopt = FusedFieldOptimizer(model.encoder, model.sigma_net, model.color_net, lr=1e-2, betas=(0.9, 0.99), eps=1e-15, init_scale=128.0,
                                    exchange=args.exchange)
-        log(f"gradient exchange: {'peer memory (fused with the optimizer)' if fopt.px is not None else ('nccl all-reduce' if world > 1 else 'none (1 GPU)')}")
+        log(f"gradient exchange: {('peer memory (fused with the optimizer) on ' + str(fopt.px.memory)) if fopt.px is not None else ('nccl all-reduce' if world > 1 else 'none (1 GPU)')}"
+            + (f" [symmetric memory unavailable: {fopt.px._symm_error}]" if fopt.px is not None and getattr(fopt.px, '_symm_error', None) else ""))
 
         from nerf_step import FusedTrainStep
         # where the next step's march is released: "start" (under this step's forward kernels, which leave registers / shared memory for
@@ -602,7 +603,8 @@ def main():
             "kernel_time_share": kern_ms / ms_eager, "kernels": breakdown,
             "cuda_graph": graphs is not None, "ms_per_step_eager_unpipelined": ms_eager / args.steps,
             "mlp_backward_kernel": args.mlp_backward,
-            "exchange": (("peer-memory reduce-scatter + sharded Adam + fp16 operand all-gather in 3 kernels + 3 flag barriers (csrc/exchange.cu)"
+            "exchange": ((f"peer-memory reduce-scatter + sharded Adam + fp16 operand all-gather in 3 launches with in-kernel flag barriers (csrc/exchange.cu); memory: {fopt.px.memory}; "
+                          + ("multimem.ld_reduce / multimem.st through the NVSwitch" if fopt.px.mc_sink else "peer loads / stores")
                           if (use_fused_opt and fopt.px is not None) else "nccl all-reduce of the fp16 sink + full optimizer pass per rank") if world > 1 else "none"),
             "pipelining": {"field_chunks": args.chunks if use_fused_opt else 1, "march_prefetch": bool(prefetch),
                            "prefetch_point": (fstep.prefetch_point if fstep is not None else None),

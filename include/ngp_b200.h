@@ -280,9 +280,12 @@ int    ngp_exchange_zero(void* my_sink, uint64_t n, ngp_stream_t stream);
  *                               flat [lo_host[i], lo_host[i] + count_host[i])), stores the fp16 operand copies into every rank's shadow,
  *                               clears the whole local bucket (n_total elements) and signals "my stores are done"
  *   ngp_exchange_finish         waits for every rank's "done", then the GradScaler update (as ngp_optim_scaler_update) */
-int    ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, uint32_t rank, uint32_t world, uint64_t lo,
-                                 uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream);
-int    ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, uint32_t rank, uint32_t world,
+/* mc_sink / mc_shadow (nullable): the same buckets / shadows addressed through ONE NVSwitch multicast mapping of all ranks' blocks (NVLS).
+ * When given, the reduction is a single multimem.ld_reduce per 16 bytes (summed inside the switch, fp32 accumulation) and the operand copies
+ * are a single multimem.st per 16 bytes (delivered to every replica) instead of `world` peer loads / stores. */
+int    ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, const void* mc_sink, uint32_t rank, uint32_t world,
+                                 uint64_t lo, uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream);
+int    ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, void* mc_shadow, uint32_t rank, uint32_t world,
                                float* const* params_host, const uint64_t* seg_off_host, const uint64_t* lo_host,
                                const uint64_t* count_host, uint32_t n_pieces, float* exp_avg_flat, float* exp_avg_sq_flat,
                                void* my_sink, uint64_t shard_lo, uint64_t shard_hi, uint64_t n_total, float lr, float beta1,
@@ -349,6 +352,9 @@ int ngp_debug_red_probe(void* table_f16x2, uint32_t entries, uint32_t blocks, ui
 /* MLP backward kernel selection: 1 = two tile contexts per CTA with a deep activation ring (default, where it fits), 0 = the
  * single-context kernel */
 int ngp_debug_set_mlp_backward(int dual);
+/* gather variant of the fused encoder -> sigma kernel (measured experiments): -1 = environment (default 0), 0 = 4-byte loads,
+ * 1 = aligned x-pair 8-byte loads, 2 = the first tma_levels table levels staged in shared memory by one cp.async.bulk per CTA */
+int ngp_debug_set_sigma_gather(int variant, int tma_levels);
 
 #ifdef __cplusplus
 }

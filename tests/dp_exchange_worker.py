@@ -46,7 +46,8 @@ def run(mode, rank, world):
     opt.gather_master()
     flat_p = torch.cat([p.detach().reshape(-1) for p in opt.params])
     out = dict(shadow=shadows[-1].cpu(), shadow1=shadows[1].cpu(), shadow0=shadows[0].cpu(), params=flat_p.cpu(), exp_avg=opt.exp_avg.cpu(), exp_avg_sq=opt.exp_avg_sq.cpu(),
-               state=opt.state.cpu(), scale=float(opt.scale_tensor().item()))
+               state=opt.state.cpu(), scale=float(opt.scale_tensor().item()),
+               memory=(opt.px.memory if opt.px is not None else "nccl"), nvls=bool(opt.px is not None and opt.px.mc_sink))
     # shadow == half(master) everywhere after the gather
     assert torch.equal(flat_p.half(), shadows[-1])
     opt.detach()

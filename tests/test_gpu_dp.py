@@ -55,10 +55,15 @@ def test_peer_exchange_matches_nccl(tmp_path):
     assert peer["scale"] == nccl["scale"] == 512.0                 # one backoff
     assert int(peer["state"][3]) == int(nccl["state"][3]) == 2      # two steps actually taken
     assert torch.equal(peer["shadow0"], peer["shadow1"])            # the skipped step changed nothing
+    # peer loads: two summands, fp32-accumulated and fp16 sums round identically and the Adam arithmetic is the same code -> identical.
+    # NVLS (multimem.ld_reduce): the sum is formed inside the NVSwitch, whose rounding of an fp16 pair sum is not RN(fp32 sum) for every
+    # input (measured here: differences of one fp16 ulp of the summed gradient on a small fraction of the entries) -> 1-ulp tolerance.
+    tol = 2e-3 if peer["nvls"] else 1e-6
     for k in ("params", "exp_avg", "exp_avg_sq"):
         a, b = peer[k].double(), nccl[k].double()
         err = float((a - b).abs().max() / b.abs().max())
-        assert err < 1e-6, (k, err)     # two summands: fp32-accumulated and fp16 sums round identically; Adam arithmetic is the same code
+        print(f"peer ({peer['memory']}) vs nccl: {k} max err {err:.3e} of max")
+        assert err < tol, (k, err)
     same = float((peer["shadow"] == nccl["shadow"]).float().mean())
-    assert same > 0.99999, same
+    assert same > (0.99 if peer["nvls"] else 0.99999), same
     print(f"peer vs nccl exchange: identical fp16 operand entries {same:.6f}")

@@ -111,3 +111,30 @@ def test_color_backward_dual_equals_single(M):
         assert torch.equal(res[(0, form)][0], res[(1, form)][0])
         assert rel_err(res[(1, form)][1].cpu().numpy(), res[(0, form)][1].cpu().numpy()) < 1e-5
         assert float(res[(1, form)][0].float().abs().sum()) > 0
+
+
+def test_sigma_forward_gather_variants_are_bit_identical():
+    """The two measured experiments of the fused encoder -> sigma kernel (aligned x-pair 8-byte gathers; coarse table levels staged in shared
+    memory by cp.async.bulk) deliver the same table entries as the default 4-byte gathers: features, hidden stash, h and sigma identical."""
+    import _ngp_b200 as nb
+    from nerf_fused import field_forward, field_cfg
+    a, b = _models()
+    M = 128 * 37 + 5
+    x = (torch.rand(M, 3, generator=gen(7)) * 2.1 - 1.05).cuda()
+    d = torch.randn(M, 3, generator=gen(8)); d = (d / d.norm(dim=-1, keepdim=True)).cuda()
+    cfg = field_cfg(b.encoder, b.sigma_net, b.color_net, b.bound, True)
+    lib = nb.load()
+    outs = []
+    try:
+        for variant, levels in ((0, 1), (1, 1), (2, 1), (2, 2)):
+            assert lib.ngp_debug_set_sigma_gather(variant, levels) == 0
+            sigma, rgb, stash = field_forward(x, d, b.encoder.embeddings, b.encoder.offsets, b.sigma_net.weights, b.color_net.weights, cfg)
+            torch.cuda.synchronize()
+            t = stash["tensors"]
+            outs.append((sigma.clone(), rgb.clone(), t[5].clone(), t[6].clone(), t[8].clone()))     # sigma, rgb, feat, h, sigma-net stash
+    finally:
+        lib.ngp_debug_set_sigma_gather(-1, 1)
+    for o in outs[1:]:
+        for ref, got in zip(outs[0], o):
+            assert torch.equal(ref, got)
+    assert float(outs[0][2].abs().max()) > 0

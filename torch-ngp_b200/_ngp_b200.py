@@ -50,8 +50,8 @@ _SIGNATURES = {
     "ngp_exchange_reduce": [_vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _vp],
     "ngp_exchange_adam": [_vp, _vp, _vp, _vp, _vp, _u32, _c.c_uint64, _c.c_uint64, _c.c_uint64, _f32, _f32, _f32, _f32, _vp, _vp],
     "ngp_exchange_zero": [_vp, _c.c_uint64, _vp],
-    "ngp_exchange_reduce_fused": [_vp, _vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _u32, _vp],
-    "ngp_exchange_adam_fused": [_vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _c.c_uint64, _c.c_uint64, _c.c_uint64,
+    "ngp_exchange_reduce_fused": [_vp, _vp, _vp, _u32, _u32, _c.c_uint64, _c.c_uint64, _vp, _u32, _vp],
+    "ngp_exchange_adam_fused": [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _c.c_uint64, _c.c_uint64, _c.c_uint64,
                                 _f32, _f32, _f32, _f32, _vp, _u32, _vp],
     "ngp_exchange_finish": [_vp, _u32, _u32, _vp, _f32, _f32, _i32, _u32, _vp],
     "ngp_composite_rays_train_forward_mse": [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -77,7 +77,7 @@ _SIGNATURES = {
     "ngp_composite_rays": [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 # every symbol include/ngp_b200.h declares (tests check the .so exports all of them)
-EXPORTED = sorted(list(_SIGNATURES) + ["ngp_debug_set_mlp_backward", "ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
+EXPORTED = sorted(list(_SIGNATURES) + ["ngp_debug_set_mlp_backward", "ngp_debug_set_sigma_gather", "ngp_last_error", "ngp_version", "ngp_build_arch", "ngp_launch_count",
                                        "ngp_reset_launch_count", "ngp_ffmlp_backward_workspace_bytes",
                                        "ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes",
                                        "ngp_peer_alloc", "ngp_peer_open", "ngp_peer_close", "ngp_peer_free", "ngp_exchange_pad_bytes",
@@ -107,6 +107,8 @@ def load():
     lib.ngp_reset_launch_count.restype = None
     lib.ngp_debug_set_mlp_backward.argtypes = [_i32]
     lib.ngp_debug_set_mlp_backward.restype = _c.c_int
+    lib.ngp_debug_set_sigma_gather.argtypes = [_i32, _i32]
+    lib.ngp_debug_set_sigma_gather.restype = _c.c_int
     lib.ngp_ffmlp_backward_workspace_bytes.argtypes = [_u32, _u32, _u32, _u32, _u32]
     lib.ngp_ffmlp_backward_workspace_bytes.restype = _sz
     for name in ("ngp_density_grid_occupied_scratch_bytes", "ngp_density_grid_update_scratch_bytes"):

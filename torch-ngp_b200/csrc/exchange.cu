@@ -45,6 +45,19 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* addr) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
     return v;
 }
+// NVLS (multicast) forms, used when the ranks' blocks are also mapped through one NVSwitch multicast object: ONE load returns the sum over
+// every replica of the addressed 16 bytes (reduced inside the switch, fp32 accumulation, one rounding to fp16), ONE store lands in every replica
+// — inbound reduce traffic and outbound operand traffic drop from (world-1)/world of the table to 1/world of it.
+__device__ __forceinline__ uint4 multimem_ld_reduce_h8(const void* mc_addr) {
+    uint4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc_addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st_16(void* mc_addr, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -224,8 +237,8 @@ __device__ __forceinline__ bool last_cta_done(uint32_t* ticket) {
 }
 
 __global__ void __launch_bounds__(256)
-k_xchg_reduce_f(PeerPtrs pads, PeerPtrs sinks, uint32_t rank, uint32_t world, size_t lo8, size_t n8, ScalerStateX* __restrict__ st,
-                unsigned long long timeout_ns) {
+k_xchg_reduce_f(PeerPtrs pads, PeerPtrs sinks, const uint4* __restrict__ mc_sink, uint32_t rank, uint32_t world, size_t lo8, size_t n8,
+                ScalerStateX* __restrict__ st, unsigned long long timeout_ns) {
     uint32_t* my_pad = reinterpret_cast<uint32_t*>(pads.p[rank]);
     const uint32_t epoch = my_pad[PAD_EPOCH + 0] + 1u;
     if (threadIdx.x < 32) {
@@ -235,6 +248,13 @@ k_xchg_reduce_f(PeerPtrs pads, PeerPtrs sinks, uint32_t rank, uint32_t world, si
     __syncthreads();
     uint4* my_sink = reinterpret_cast<uint4*>(sinks.p[rank]);
     bool bad = false;
+    if (mc_sink) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+            const uint4 o = multimem_ld_reduce_h8(mc_sink + lo8 + i);
+            bad |= half2_nonfinite(o.x) | half2_nonfinite(o.y) | half2_nonfinite(o.z) | half2_nonfinite(o.w);
+            my_sink[lo8 + i] = o;
+        }
+    } else
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint4 v[MAX_WORLD];
@@ -270,7 +290,7 @@ struct AdamPieces {            // the pieces of this rank's shard, one per param
 };
 
 __global__ void __launch_bounds__(256)
-k_xchg_adam_f(PeerPtrs pads, PeerPtrs shadows, uint32_t rank, uint32_t world, AdamPieces pieces, float* __restrict__ m, float* __restrict__ v,
+k_xchg_adam_f(PeerPtrs pads, PeerPtrs shadows, uint4* __restrict__ mc_shadow, uint32_t rank, uint32_t world, AdamPieces pieces, float* __restrict__ m, float* __restrict__ v,
               uint4* __restrict__ sink, size_t shard_lo8, size_t shard_hi8, size_t total8, float lr, float beta1, float beta2, float eps,
               ScalerStateX* __restrict__ st, unsigned long long timeout_ns) {
     __shared__ uint32_t s_skip;
@@ -326,9 +346,13 @@ k_xchg_adam_f(PeerPtrs pads, PeerPtrs shadows, uint32_t rank, uint32_t world, Ad
                 shw[2 * q] = *reinterpret_cast<const uint32_t*>(&s01);
                 shw[2 * q + 1] = *reinterpret_cast<const uint32_t*>(&s23);
             }
+            if (mc_shadow) {
+                multimem_st_16(mc_shadow + f8, sh);
+            } else {
 #pragma unroll
-            for (uint32_t q = 0; q < MAX_WORLD; ++q)
-                if (q < world) reinterpret_cast<uint4*>(shadows.p[q])[f8] = sh;
+                for (uint32_t q = 0; q < MAX_WORLD; ++q)
+                    if (q < world) reinterpret_cast<uint4*>(shadows.p[q])[f8] = sh;
+            }
         }
     }
     // the other ranks' shards of my bucket: everybody has read them (barrier 1), clear them for the next step
@@ -475,8 +499,8 @@ extern "C" int ngp_exchange_zero(void* my_sink, uint64_t n, ngp_stream_t stream)
 }
 
 // ---- fused form: three launches per step (see the kernels' comment) ----
-extern "C" int ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, uint32_t rank, uint32_t world, uint64_t lo,
-                                         uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream) {
+extern "C" int ngp_exchange_reduce_fused(void* const* pads_host, void* const* sinks_host, const void* mc_sink, uint32_t rank, uint32_t world,
+                                         uint64_t lo, uint64_t count, void* state, uint32_t timeout_ms, ngp_stream_t stream) {
     PeerPtrs pp, sp;
     int rc = fill_ptrs(pp, pads_host, world, "exchange_reduce_fused");
     if (rc) return rc;
@@ -484,14 +508,14 @@ extern "C" int ngp_exchange_reduce_fused(void* const* pads_host, void* const* si
     if (rc) return rc;
     if (rank >= world || (lo & 7) || (count & 7) || !state) return fail(NGP_EINVAL, "exchange_reduce_fused: bad arguments");
     // every CTA spins on the ranks' flags before it reduces: the grid must be co-resident (<= 8 CTAs of 256 threads per SM)
-    k_xchg_reduce_f<<<grid_for(count / 8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sp, rank, world, lo / 8, count / 8, (ScalerStateX*)state,
+    k_xchg_reduce_f<<<grid_for(count / 8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sp, (const uint4*)mc_sink, rank, world, lo / 8, count / 8, (ScalerStateX*)state,
                                                                              (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull);
     return check_launch("exchange_reduce_fused");
 }
 
 // params_host / seg_off_host / lo_host / count_host: n_pieces (<= 4) parameter pieces of this rank's shard [shard_lo, shard_hi);
 // n_total = size of the flat bucket.  Also clears the bucket and signals completion of the shadow stores.
-extern "C" int ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, uint32_t rank, uint32_t world,
+extern "C" int ngp_exchange_adam_fused(void* const* pads_host, void* const* shadows_host, void* mc_shadow, uint32_t rank, uint32_t world,
                                        float* const* params_host, const uint64_t* seg_off_host, const uint64_t* lo_host,
                                        const uint64_t* count_host, uint32_t n_pieces, float* exp_avg_flat, float* exp_avg_sq_flat,
                                        void* my_sink, uint64_t shard_lo, uint64_t shard_hi, uint64_t n_total, float lr, float beta1,
@@ -513,7 +537,7 @@ extern "C" int ngp_exchange_adam_fused(void* const* pads_host, void* const* shad
         pc.p[i] = params_host[i]; pc.seg_off[i] = seg_off_host[i]; pc.lo8[i] = lo_host[i] / 8; pc.n8[i] = count_host[i] / 8;
         work8 += count_host[i] / 8;
     }
-    k_xchg_adam_f<<<grid_for(work8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sh, rank, world, pc, exp_avg_flat, exp_avg_sq_flat, (uint4*)my_sink,
+    k_xchg_adam_f<<<grid_for(work8 + 1, 4), 256, 0, as_stream(stream)>>>(pp, sh, (uint4*)mc_shadow, rank, world, pc, exp_avg_flat, exp_avg_sq_flat, (uint4*)my_sink,
                                                                         shard_lo / 8, shard_hi / 8, n_total / 8, lr, beta1, beta2, eps,
                                                                         (ScalerStateX*)state,
                                                                         (unsigned long long)(timeout_ms ? timeout_ms : 2000u) * 1000000ull);

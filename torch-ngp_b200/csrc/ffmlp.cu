@@ -65,7 +65,10 @@ struct FieldArgs {
     uint32_t gridtype;
     int align_corners;
     __half* feat_out;        // [M, 2L] stash (nullable)
-    int pair_loads;          // IN_GRID gathers: 8-byte loads of aligned x-pairs (see write_grid_row)
+    int gather_variant;      // IN_GRID gathers: 0 = 4-byte loads (default), 1 = aligned x-pair 8-byte loads, 2 = coarse levels from shared memory
+    uint32_t tma_levels;     // IN_GRID: the first tma_levels levels of the table are staged in shared memory by one bulk async copy
+    uint32_t tma_bytes;      //   (their bytes, a multiple of 16; the staged image starts at table entry 0)
+    uint32_t tma_smem_off;   //   byte offset of the staged image from the 1024-aligned dynamic shared memory base
     // IN_SHGEO (and the color backward)
     const float* dirs;       // [M,3]
     const __half* h_sigma;   // [M,16]
@@ -143,8 +146,22 @@ struct LevelParams { uint32_t off, size, res; float scale; };
 
 // hash-grid features of one sample -> swizzled tile row (+ optional global stash); D=3, C=2, fp16 table, linear interp
 // (`xin` = the sample's coordinates, loaded by the caller one tile ahead so the gathers do not wait on them)
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// Gather variants (FieldArgs::gather_variant; the default 0 is what ships, 1 and 2 are measured experiments kept behind environment
+// switches — each variant is straight-line code of its own so that the 32 gathers of a 4-level chunk stay back to back):
+//   0  32 independent 4-byte loads per chunk (read-only path)
+//   1  x-adjacent corner pairs: ONE 8-byte load of the aligned entry pair that holds corner 2j also delivers corner 2j+1 whenever the
+//      two entries are that pair (dense level with an even index, hashed level with an even x: half of all cases); only otherwise a
+//      second, predicated 4-byte load
+//   2  the first fa.tma_levels levels are read from the shared-memory image staged by cp.async.bulk (TMA-class bulk copy)
+template <int V>
 __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, bool ok, const FieldArgs& fa,
-                                               const LevelParams* __restrict__ lv, size_t row, const float (&xin)[3]) {
+                                               const LevelParams* __restrict__ lv, size_t row, const float (&xin)[3],
+                                               const uint32_t tab_smem = 0u) {
     float x[3] = {0.5f, 0.5f, 0.5f};
     bool oob = !ok;
     if (ok) {
@@ -163,36 +180,83 @@ __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, b
             // thread is the only one working on its sample, so the loads must overlap each other)
             float pos[4][3];
             uint32_t vals[4][8];
+            if constexpr (V == 1) {
+                uint32_t cidx[4][8];
+                const uint32_t* lvl[4];
 #pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) {
-                const LevelParams P = lv[ch * 4 + q];
-                uint32_t pg[3];
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const LevelParams P = lv[ch * 4 + q];
+                    uint32_t pg[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    pos[q][d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
-                    pg[d] = (uint32_t)floorf(pos[q][d]);
-                    pos[q][d] -= (float)pg[d];
+                    for (int d = 0; d < 3; ++d) {
+                        pos[q][d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
+                        pg[d] = (uint32_t)floorf(pos[q][d]);
+                        pos[q][d] -= (float)pg[d];
+                    }
+                    corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx[q]);
+                    lvl[q] = reinterpret_cast<const uint32_t*>(fa.table) + P.off;      // level bases are even entries (offsets % 8 == 0)
                 }
-                uint32_t cidx[8];
-                corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
-                const uint32_t* lvl = reinterpret_cast<const uint32_t*>(fa.table) + P.off;
-                if (fa.pair_loads && (P.off & 1u) == 0u) {
-                    // corners 2j / 2j+1 differ only in x.  ONE 8-byte load of the aligned entry pair that holds corner 2j also
-                    // delivers corner 2j+1 whenever the two entries are that pair (dense level with an even index, hashed level
-                    // with an even x: half of all cases); only otherwise a second 4-byte load is issued (predicated, never a third
-                    // one).  The kernel is bound by L1 wavefronts (ncu r2: l1tex 69 %, every 4-byte corner load of a fine level is
-                    // a wavefront of its own): this removes a quarter of them.  Same values, same blend order.
+                uint2 a[4][4];
+                uint32_t b[4][4];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q)
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) a[q][j] = __ldg(reinterpret_cast<const uint2*>(lvl[q] + (cidx[q][2 * j] & ~1u)));
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q)
 #pragma unroll
                     for (uint32_t j = 0; j < 4; ++j) {
-                        const uint32_t i0 = cidx[2 * j], i1 = cidx[2 * j + 1];
-                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(lvl + (i0 & ~1u)));
-                        const bool hi0 = (i0 & 1u) != 0u;
-                        vals[q][2 * j] = hi0 ? a.y : a.x;
-                        uint32_t b = hi0 ? a.x : a.y;
-                        if ((i0 ^ i1) != 1u) b = __ldg(lvl + i1);
-                        vals[q][2 * j + 1] = b;
+                        b[q][j] = 0u;
+                        if ((cidx[q][2 * j] ^ cidx[q][2 * j + 1]) != 1u) b[q][j] = __ldg(lvl[q] + cidx[q][2 * j + 1]);
                     }
-                } else {
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q)
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        const bool hi0 = (cidx[q][2 * j] & 1u) != 0u;
+                        const bool adj = (cidx[q][2 * j] ^ cidx[q][2 * j + 1]) == 1u;
+                        vals[q][2 * j] = hi0 ? a[q][j].y : a[q][j].x;
+                        vals[q][2 * j + 1] = adj ? (hi0 ? a[q][j].x : a[q][j].y) : b[q][j];
+                    }
+            } else if (V == 2 && ch * 4 < fa.tma_levels) {
+                // the chunk that holds staged levels (normally only chunk 0): per level, shared memory or global
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const LevelParams P = lv[ch * 4 + q];
+                    uint32_t pg[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        pos[q][d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
+                        pg[d] = (uint32_t)floorf(pos[q][d]);
+                        pos[q][d] -= (float)pg[d];
+                    }
+                    uint32_t cidx[8];
+                    corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
+                    if (ch * 4 + q < fa.tma_levels) {
+                        // this level's entries sit in shared memory (staged once per CTA by cp.async.bulk): same values, no L1 / L2 traffic
+                        const uint32_t lbase = tab_smem + P.off * 4u;
+#pragma unroll
+                        for (uint32_t i = 0; i < 8; ++i) vals[q][i] = ld_shared_u32(lbase + cidx[i] * 4u);
+                    } else {
+                        const uint32_t* lvl = reinterpret_cast<const uint32_t*>(fa.table) + P.off;
+#pragma unroll
+                        for (uint32_t i = 0; i < 8; ++i) vals[q][i] = __ldg(lvl + cidx[i]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const LevelParams P = lv[ch * 4 + q];
+                    uint32_t pg[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        pos[q][d] = fmaf(x[d], P.scale, fa.align_corners ? 0.0f : 0.5f);
+                        pg[d] = (uint32_t)floorf(pos[q][d]);
+                        pos[q][d] -= (float)pg[d];
+                    }
+                    uint32_t cidx[8];
+                    corner_indices<3>(fa.gridtype, fa.align_corners != 0, P.size, P.res, pg, cidx);
+                    const uint32_t* lvl = reinterpret_cast<const uint32_t*>(fa.table) + P.off;
 #pragma unroll
                     for (uint32_t i = 0; i < 8; ++i) vals[q][i] = __ldg(lvl + cidx[i]);
                 }
@@ -218,7 +282,7 @@ __device__ __forceinline__ void write_grid_row(uint32_t tile_addr, uint32_t r, b
 }
 
 // ================================ forward / inference ==========================================
-template <bool TRAIN, uint32_t ACT, int IN_MODE = IN_PLAIN, int OUT_MODE = OUT_PLAIN>
+template <bool TRAIN, uint32_t ACT, int IN_MODE = IN_PLAIN, int OUT_MODE = OUT_PLAIN, int GATHER = 0>
 __global__ void __launch_bounds__(128)
 k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ weights,
                 __half* __restrict__ forward_buffer, __half* __restrict__ outputs, const uint32_t B_arg,
@@ -246,7 +310,22 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
     const uint32_t w_addr = base + A_TILE_BYTES;
     const uint32_t nmat = num_layers + 1;
 
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __shared__ __align__(8) uint64_t tbar;
+    const uint32_t tab_smem = base + fa.tma_smem_off;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        if constexpr (IN_MODE == IN_GRID) mbar_init(&tbar, 1);
+        mbar_fence_init();
+        if constexpr (IN_MODE == IN_GRID) {
+            if (fa.tma_levels) {
+                // TMA-class bulk copy (cp.async.bulk, SASS UBLKCP): the dense coarse levels of the fp16 table, contiguous from entry 0,
+                // global -> shared in ONE instruction issued by one thread; completion is a transaction count on an mbarrier
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&tbar)), "r"(fa.tma_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(tab_smem), "l"(fa.table), "r"(fa.tma_bytes), "r"(smem_u32(&tbar)) : "memory");
+            }
+        }
+    }
     if (warp == 0) tmem_alloc<64>(&tmem_base_s);
 
     // stage all weight matrices (K-major B operands: row n = output neuron, 128-byte pitch)
@@ -266,6 +345,9 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t t_lane = tmem_base + ((warp * 32u) << 16);
     uint32_t phase = 0;
+    if constexpr (IN_MODE == IN_GRID) {
+        if (fa.tma_levels) mbar_wait(&tbar, 0);       // the staged levels have landed (async-proxy writes, made visible by the mbarrier)
+    }
 
     const uint32_t ntiles = (B + TILE_M - 1) / TILE_M;
     // IN_GRID: the coordinates of the next tile's sample are loaded a tile ahead (the gathers depend on them)
@@ -306,7 +388,7 @@ k_ffmlp_forward(const __half* __restrict__ inputs, const __half* __restrict__ we
         if constexpr (IN_MODE == IN_GRID) {
             const float cur_x[3] = {nx_x[0], nx_x[1], nx_x[2]};
             preload_xyz(tile + gridDim.x);
-            write_grid_row(a_addr, tid, row_ok, fa, lv, row, cur_x);
+            write_grid_row<GATHER>(a_addr, tid, row_ok, fa, lv, row, cur_x, tab_smem);
         }
         else if constexpr (IN_MODE == IN_SHGEO) {
             const float cd0 = nx_d[0], cd1 = nx_d[1], cd2 = nx_d[2];
@@ -1391,6 +1473,8 @@ static int set_smem(K kernel, size_t bytes, const char* who) {
 
 // two-context backward (k_ffmlp_backward_dual): shared memory it needs, or 0 when the configuration does not fit one SM
 static int g_mlp_backward_dual = 1;      // ngp_debug_set_mlp_backward(): A/B switch for tests and benchmarks
+static int g_sigma_gather = -1;          // ngp_debug_set_sigma_gather(): -1 = environment (NGP_SIGMA_PAIR_LOADS / NGP_SIGMA_TMA_LEVELS), else 0 / 1 / 2
+static int g_sigma_tma_levels = 1;
 static size_t dual_backward_smem(uint32_t in_dim, uint32_t num_layers, bool want_dx) {
     const size_t w = (size_t)num_layers * W_SLOT_BYTES + (want_dx ? (size_t)in_dim * 128 : 0);
     const size_t need = 1024 + w + 2 * (size_t)(2 + num_layers + 1) * A_TILE_BYTES;
@@ -1587,29 +1671,62 @@ static int field_sigma_forward_impl(const float* x01, float bound, const uint32_
     fa.S = S; fa.H = H; fa.gridtype = gridtype; fa.align_corners = align_corners; fa.feat_out = (__half*)feat_out;
     fa.sigma_out = sigma_out;
     static const int pair_env = [] { const char* e = getenv("NGP_SIGMA_PAIR_LOADS"); return (e && e[0] == '1') ? 1 : 0; }();
-    fa.pair_loads = pair_env && (reinterpret_cast<uintptr_t>(table_f16) & 7u) == 0;
-    const size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
+    const bool want_pair = g_sigma_gather >= 0 ? g_sigma_gather == 1 : pair_env != 0;
+    fa.gather_variant = (want_pair && (reinterpret_cast<uintptr_t>(table_f16) & 7u) == 0) ? 1 : 0;
+    size_t smem = 1024 + A_TILE_BYTES + (size_t)(num_layers + 1) * W_SLOT_BYTES;
+    // NGP_SIGMA_TMA_LEVELS=k (default 0 = off): stage the first k levels of the table in shared memory with one cp.async.bulk per CTA
+    // (north_star: "TMA-staged embedding tiles").  The caller passes the level sizes through tma_level_bytes (host copy of offsets).
+    static const uint32_t tma_env = [] { const char* e = getenv("NGP_SIGMA_TMA_LEVELS"); return e ? (uint32_t)atoi(e) : 0u; }();
+    uint32_t ctas_per_sm = 3;
+    const uint32_t want_tma = g_sigma_gather >= 0 ? (g_sigma_gather == 2 ? (uint32_t)g_sigma_tma_levels : 0u) : tma_env;
+    if (want_tma && !want_pair && (reinterpret_cast<uintptr_t>(table_f16) & 15u) == 0) {
+        // experiment switch only: the level offsets are read back once (synchronous 4 (L+1)-byte copy on the first call, i.e. during warm-up)
+        static const int32_t* cached_ptr = nullptr;
+        static int32_t cached_off[65];
+        if (cached_ptr != offsets && L <= 64) {
+            if (cudaMemcpy(cached_off, offsets, sizeof(int32_t) * (L + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
+                return fail(NGP_ECUDA, "field_sigma_forward: cannot read the level offsets");
+            cached_ptr = offsets;
+        }
+        const uint32_t k = want_tma < L ? want_tma : L;
+        const size_t tb = L <= 64 ? (((size_t)cached_off[k] * 4 + 15) & ~(size_t)15) : 0;
+        if (tb > 0 && smem + tb <= 227 * 1024) {
+            fa.gather_variant = 2;
+            fa.tma_levels = k; fa.tma_bytes = (uint32_t)tb; fa.tma_smem_off = (uint32_t)(smem - 1024);
+            smem += tb;
+            const uint32_t fit = (uint32_t)((227 * 1024) / (smem + 1024));
+            ctas_per_sm = fit < 3 ? (fit ? fit : 1) : 3;
+        }
+    }
     // The kernel is bound by its table gathers (128 per sample), i.e. by L1 hit rate and L2->L1 sector traffic.  Shared memory and
     // L1 share 256 KB per SM: at the occupancy the registers allow (5 CTAs x 42 KB) the driver carves 228 KB for shared memory and
     // leaves 28 KB of L1.  Three resident CTAs with a 132 KB carve-out leave ~124 KB of L1 for the coarse levels' entries and run
     // faster (measured at 640k rays: 5 CTAs 1.17 ms, 4 CTAs + 196 KB 1.06 ms, 3 CTAs + 132 KB 1.05 ms).
-    constexpr uint32_t SIGMA_CTAS_PER_SM = 3;
+    const uint32_t SIGMA_CTAS_PER_SM = ctas_per_sm;
     const uint32_t grid = persistent_grid((M + TILE_M - 1) / TILE_M, SIGMA_CTAS_PER_SM);
     cudaStream_t st = as_stream(stream);
     const int carveout_pct = (int)((SIGMA_CTAS_PER_SM * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-    if (train) cudaFuncSetAttribute(k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
-    else cudaFuncSetAttribute(k_ffmlp_forward<false, ACT_RELU, IN_GRID, OUT_SIGMA>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_pct);
+#define NGP_LAUNCH_SIGMA_FWD(TR, GV)                                                                                                   \
+    do {                                                                                                                               \
+        cudaFuncSetAttribute(k_ffmlp_forward<TR, ACT_RELU, IN_GRID, OUT_SIGMA, GV>, cudaFuncAttributePreferredSharedMemoryCarveout,    \
+                             carveout_pct);                                                                                            \
+        rc = set_smem(k_ffmlp_forward<TR, ACT_RELU, IN_GRID, OUT_SIGMA, GV>, smem, "field_sigma_forward");                             \
+        if (rc) return rc;                                                                                                             \
+        k_ffmlp_forward<TR, ACT_RELU, IN_GRID, OUT_SIGMA, GV><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights,                \
+                                                                                     (__half*)((TR) ? forward_buffer : nullptr),      \
+                                                                                     (__half*)h_out, M, in_dim, num_layers, fa);       \
+    } while (0)
+    // the default gather variant is its own kernel instantiation: the experiment variants cannot disturb its code generation
     if (train) {
-        rc = set_smem(k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA>, smem, "field_sigma_forward");
-        if (rc) return rc;
-        k_ffmlp_forward<true, ACT_RELU, IN_GRID, OUT_SIGMA><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, (__half*)forward_buffer,
-                                                                                  (__half*)h_out, M, in_dim, num_layers, fa);
+        if (fa.gather_variant == 0) NGP_LAUNCH_SIGMA_FWD(true, 0);
+        else if (fa.gather_variant == 1) NGP_LAUNCH_SIGMA_FWD(true, 1);
+        else NGP_LAUNCH_SIGMA_FWD(true, 2);
     } else {
-        rc = set_smem(k_ffmlp_forward<false, ACT_RELU, IN_GRID, OUT_SIGMA>, smem, "field_sigma_forward");
-        if (rc) return rc;
-        k_ffmlp_forward<false, ACT_RELU, IN_GRID, OUT_SIGMA><<<grid, 128, smem, st>>>(nullptr, (const __half*)weights, nullptr,
-                                                                                   (__half*)h_out, M, in_dim, num_layers, fa);
+        if (fa.gather_variant == 0) NGP_LAUNCH_SIGMA_FWD(false, 0);
+        else if (fa.gather_variant == 1) NGP_LAUNCH_SIGMA_FWD(false, 1);
+        else NGP_LAUNCH_SIGMA_FWD(false, 2);
     }
+#undef NGP_LAUNCH_SIGMA_FWD
     return check_launch("field_sigma_forward");
 }
 
@@ -1745,6 +1862,13 @@ extern "C" int ngp_ffmlp_free_splitk(void) { return NGP_OK; }
 
 // A/B switch (tests, benchmarks): 1 = two-context MLP backward where it fits (default), 0 = single-context kernel
 extern "C" int ngp_debug_set_mlp_backward(int dual) { g_mlp_backward_dual = dual ? 1 : 0; return NGP_OK; }
+// gather variant of the fused encoder -> sigma kernel: -1 = as the environment says (default 0), 0 = 4-byte loads, 1 = aligned x-pair
+// 8-byte loads, 2 = the first tma_levels levels staged in shared memory by cp.async.bulk
+extern "C" int ngp_debug_set_sigma_gather(int variant, int tma_levels) {
+    if (variant < -1 || variant > 2 || tma_levels < 1) return fail(NGP_EINVAL, "debug_set_sigma_gather: variant in [-1, 2], tma_levels >= 1");
+    g_sigma_gather = variant; g_sigma_tma_levels = tma_levels;
+    return NGP_OK;
+}
 
 // test hook, not part of the reference ABI
 extern "C" int ngp_debug_umma(const void* A, const void* Bm, float* D, int mode, ngp_stream_t stream) {

@@ -161,6 +161,57 @@ class PeerExchange:
         seg = (2 * self.n + 255) // 256 * 256
         self._pad_bytes, self._seg_bytes = pad, seg
         total = pad + 2 * seg
+        self._symm = None
+        self.mc_sink = self.mc_shadow = None
+        self.memory = None
+        import os
+        mode = os.environ.get("NGP_EXCHANGE_MEM", "auto")        # auto | symm | ipc
+        if mode in ("auto", "symm"):
+            # torch's symmetric-memory allocator (plumbing): cuMem allocations exchanged between the ranks AND bound to one NVSwitch
+            # multicast object, which is what the NVLS forms of the exchange kernels need (multimem.ld_reduce / multimem.st)
+            try:
+                self._init_symm(total, pad, seg, group, dev)
+            except Exception as e:
+                if mode == "symm":
+                    raise
+                self._symm = None
+                self._symm_error = f"{type(e).__name__}: {e}"
+        # every rank must end up on the same kind of memory
+        ok = torch.tensor([1 if self._symm is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self._symm = None
+            self.mc_sink = self.mc_shadow = None
+            self._init_ipc(total, pad, seg, group, dev)
+        arr = ctypes.c_void_p * self.world
+        self.pads = arr(*[b for b in self._base])
+        self.sinks = arr(*[b + pad for b in self._base])
+        self.shadows = arr(*[b + pad + seg for b in self._base])
+        assert self.sink.data_ptr() == self._base[self.rank] + pad and self.sink.dtype == torch.half
+        self.bounds = shard_bounds(self.n, self.world)
+        dist.barrier(group=group)        # every rank has mapped every block before anyone signals into it
+
+    def _init_symm(self, total, pad, seg, group, dev):
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(buf, grp)
+        buf.zero_()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        self._base = [int(p) for p in hdl.buffer_ptrs]
+        assert self._base[self.rank] == buf.data_ptr()
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        if mc:
+            self.mc_sink, self.mc_shadow = mc + pad, mc + pad + seg
+        self.sink = buf[pad:pad + 2 * self.n].view(torch.half)
+        self.shadow = buf[pad + seg:pad + seg + 2 * self.n].view(torch.half)
+        self._symm = (buf, hdl)
+        self.memory = "torch symmetric memory" + (" + NVSwitch multicast (NVLS)" if mc else " (no multicast)")
+
+    def _init_ipc(self, total, pad, seg, group, dev):
+        import ctypes
+        lib = self._lib
         ptr = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(dev):
@@ -179,16 +230,10 @@ class PeerExchange:
                 if rc != 0:
                     raise RuntimeError(f"ngp_peer_open(rank {r}) failed ({rc}): {lib.ngp_last_error().decode()}")
                 self._base[r] = int(p.value)
-        arr = ctypes.c_void_p * self.world
-        self.pads = arr(*[b for b in self._base])
-        self.sinks = arr(*[b + pad for b in self._base])
-        self.shadows = arr(*[b + pad + seg for b in self._base])
         self._raw = (_RawCuda(self._base[self.rank] + pad, self.n, "<f2"), _RawCuda(self._base[self.rank] + pad + seg, self.n, "<f2"))
         self.sink = torch.as_tensor(self._raw[0], device=dev)
         self.shadow = torch.as_tensor(self._raw[1], device=dev)
-        assert self.sink.data_ptr() == self._base[self.rank] + pad and self.sink.dtype == torch.half
-        self.bounds = shard_bounds(self.n, self.world)
-        dist.barrier(group=group)        # every rank has mapped every block before anyone signals into it
+        self.memory = "cudaMalloc + CUDA IPC (library-owned)"
 
     @property
     def my_range(self):
@@ -218,6 +263,11 @@ class PeerExchange:
             dist.barrier(group=self.group)
         except Exception:
             pass
+        if self._symm is not None:
+            self.sink = self.shadow = None
+            self._symm = None
+            self._base = None
+            return
         for r, b in enumerate(self._base):
             if r != self.rank and b:
                 self._lib.ngp_peer_close(ctypes.c_void_p(b))

@@ -162,8 +162,8 @@ class FusedFieldOptimizer:
             self._fused_args = (P, seg, los, cnt, n)
         P, seg, los, cnt, n = self._fused_args
         tmo = 20000
-        _backend.call("ngp_exchange_reduce_fused", px.pads, px.sinks, px.rank, px.world, lo, hi - lo, self.state.data_ptr(), tmo)
-        _backend.call("ngp_exchange_adam_fused", px.pads, px.shadows, px.rank, px.world, P, seg, los, cnt, n, self.exp_avg.data_ptr(),
+        _backend.call("ngp_exchange_reduce_fused", px.pads, px.sinks, px.mc_sink, px.rank, px.world, lo, hi - lo, self.state.data_ptr(), tmo)
+        _backend.call("ngp_exchange_adam_fused", px.pads, px.shadows, px.mc_shadow, px.rank, px.world, P, seg, los, cnt, n, self.exp_avg.data_ptr(),
                       self.exp_avg_sq.data_ptr(), self.sink.data_ptr(), lo, hi, self.sink.numel(), float(self.lr), float(self.betas[0]),
                       float(self.betas[1]), float(self.eps), self.state.data_ptr(), tmo)
         _backend.call("ngp_exchange_finish", px.pads, px.rank, px.world, self.state.data_ptr(), float(self.growth), float(self.backoff),
