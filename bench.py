@@ -149,6 +149,12 @@ def units_of(name, args):
     if name == "ngp_composite_rays_train_forward":
         M, N = args[4], args[5]
         return N, 24 * M + 32 * N, 0
+    if name == "ngp_composite_rays_train_forward_mse":
+        M, N = args[4], args[5]
+        return N, 24 * M + (32 + 12 + 12 + 4 + 4) * N, 0         # + target read, g_image / g_ws / sqerr written
+    if name == "ngp_exchange_reduce_fused":
+        world, count = args[4], args[6]
+        return count, count * 2 * (world + 1), 0                  # my shard read from every rank's bucket, reduced copy written
     if name == "ngp_composite_rays_train_backward":
         M, N = args[8], args[9]
         return N, 40 * M + 44 * N, 0
@@ -641,7 +647,7 @@ def main():
             ach = ops_per_launch / (gb["ms"] / gb["calls"] * 1e-3) / 1e9
             line_red.update({"kernel": "ngp_grid_encode_backward", "red_ops_per_sample": red_per_sample, "achieved_gops": ach,
                              "frac_of_measured_8B_rate": ach / rates["v2_f16x2_8B"],
-                             "source": "red ops per sample = lts__t_sectors_srcunit_tex_op_red.sum / rows of the ncu --set full capture (profiles/r2_ncu_step.md)"})
+                             "source": "red ops per sample = lts__t_sectors_srcunit_tex_op_red.sum / rows of the ncu --set full capture (profiles/r2c_ncu_step.md)"})
         line["l2_reduction_roofline"] = line_red
         del probe_tab
     except Exception as e:

@@ -19,7 +19,14 @@ METRICS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", 
            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
            "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 ENTRY = {"k_grid_backward": "ngp_grid_encode_backward", "k_ffmlp_backward_fused<0, 0>": "ngp_ffmlp_backward",
-         "k_ffmlp_backward_fused<0, 1>": "ngp_field_color_backward"}
+         "k_ffmlp_backward_fused<0, 1>": "ngp_field_color_backward", "k_ffmlp_backward_dual<0, 0>": "ngp_ffmlp_backward_ex",
+         "k_ffmlp_backward_dual<0, 1>": "ngp_field_color_backward_ex", "k_ffmlp_forward<1, 0, 1, 1": "ngp_field_sigma_forward",
+         "k_ffmlp_forward<1, 0, 2, 2": "ngp_field_color_forward", "k_march_rays_train": "ngp_march_rays_train",
+         "k_composite_train_fwd": "ngp_composite_rays_train_forward_mse", "k_composite_train_bwd": "ngp_composite_rays_train_backward"}
+EXTRA = ["lts__t_sectors_srcunit_tex_op_red.sum", "lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed",
+         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+         "smsp__inst_executed_op_global_red.sum", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]
 
 
 def to_bytes(v, unit):
@@ -38,8 +45,8 @@ def rep(path, out, title, samples=None, traffic_json=None):
     for r in data:
         name = r[col["Kernel Name"]]
         lines.append(f"## {name[:110]}\n")
-        for m in METRICS:
-            if m in col:
+        for m in METRICS + EXTRA:
+            if m in col and r[col[m]] not in ("", "n/a"):
                 lines.append(f"- {m}: {r[col[m]]} {units[col[m]]}")
         st = []
         for h, i in stall_cols:
@@ -57,6 +64,10 @@ def rep(path, out, title, samples=None, traffic_json=None):
                     b = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
                         to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
                     traffic[entry] = {"dram_bytes_per_sample": b / samples, "samples": samples, "source": f"{out} ({path.split('/')[-1]})"}
+                    red = "lts__t_sectors_srcunit_tex_op_red.sum"
+                    if key == "k_grid_backward" and red in col:
+                        traffic[entry]["red_ops_per_sample"] = float(r[col[red]].replace(",", "")) / samples
+                        traffic[entry]["l2_red_sector_pct_of_peak"] = float(r[col["lts__t_sectors_srcunit_tex_op_red.avg.pct_of_peak_sustained_elapsed"]].replace(",", ""))
     open(out, "w").write("\n".join(lines) + "\n")
     if traffic_json and traffic:
         json.dump(traffic, open(traffic_json, "w"), indent=1)
