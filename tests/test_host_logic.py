@@ -107,3 +107,35 @@ def test_staged_reference_python_runs_over_the_dropin_packages():
     with st.active():
         net = sdf.SDFNetwork()
     assert net.backbone.weights.shape == (64 * (32 + 64 * 2 + 16),)
+
+
+def test_deferred_tensor_materialises_in_the_producers_grad_mode():
+    """ngp_lazy: a deferred encoder output created under torch.no_grad() must not build an autograd graph when a consumer outside the
+    no_grad block forces it (this broke __graft_entry__.smoke(): `with torch.no_grad(): f = encoder(x)` ... `f.float().numpy()`)."""
+    import warnings
+    import torch
+    import ngp_lazy
+
+    class _D(ngp_lazy.Deferred):
+        def _compute(self):
+            return self._param * 2.0
+
+    p = torch.nn.Parameter(torch.ones(4, 3))
+
+    def make():
+        t = ngp_lazy.Deferred._wrap(_D, [4, 3], torch.float32, "cpu")
+        t._param, t._value = p, None
+        return t
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")           # torch.autocast('cuda') on a CPU-only box warns and stays disabled
+        with torch.no_grad():
+            a = make()
+        va = a.float()
+        assert not va.requires_grad and va.grad_fn is None
+        assert float(va.sum()) == 24.0
+        va.numpy()                                 # would raise on a tensor that requires grad
+        b = make()                                 # created with grad enabled: the graph is built as for the eager op
+        with torch.no_grad():
+            vb = b.materialize()
+        assert vb.requires_grad

@@ -358,53 +358,81 @@ struct MseArgs {             // optional loss head of k_composite_train_fwd (tar
     float* sqerr;            // [N]   squared error per row of the rays table
 };
 
+// G = lanes per ray (8, 16 or 32).  The bench scene has 8 samples per ray on average (most rays that hit anything carry 10-30, half of the
+// rays none): with one warp per ray three quarters of the lanes idle and the kernels are latency-bound (ncu r2c: long-scoreboard 61-72 %,
+// issue 38-69 %).  A group of G lanes owns a ray and walks it G samples at a time; the 32 / G groups of a warp iterate together until the
+// longest of their rays is done (rays of a warp are neighbours in the rays table, i.e. similar lengths).  Same arithmetic per sample, the scans are
+// G wide (different re-association than the 32-wide form, same tolerance).
+template <int G> __device__ __forceinline__ float grp_incl_prod(float v, uint32_t gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o, G); if (gl >= (uint32_t)o) v *= t; }
+    return v;
+}
+template <int G> __device__ __forceinline__ float grp_incl_sum(float v, uint32_t gl) {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, v, o, G); if (gl >= (uint32_t)o) v += t; }
+    return v;
+}
+template <int G> __device__ __forceinline__ float grp_sum(float v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G>
 __global__ void __launch_bounds__(128)
 k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
                       const float* __restrict__ deltas, const int* __restrict__ rays, uint32_t M, uint32_t N,
                       float T_thresh, float* __restrict__ weights_sum, float* __restrict__ depth,
                       float* __restrict__ image, const MseArgs mse) {
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t GMASK = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per row of the rays table
-    if (n >= N) return;                                                   // warp-uniform
-    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], cnt = rays[n * 3 + 2];
-    float r = 0, g = 0, b = 0, ws = 0, d = 0;
-    if (cnt != 0 && offset + cnt <= M) {                                  // empty / dropped ray: outputs stay 0
-        const float* __restrict__ sg = sigmas + offset;
-        const float* __restrict__ cl = rgbs + (size_t)offset * 3;
-        const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
-        float T = 1.0f, t_acc = 0.f;
-        float pr = 0, pg = 0, pb = 0, pws = 0, pd = 0;                   // per-lane partial sums
-        for (uint32_t base = 0; base < cnt; base += 32) {
-            const uint32_t i = base + lane;
-            const bool valid = i < cnt;
-            float alpha = 0.f, d1 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-            if (valid) {
-                const float2 dd = __ldg(dl + i);
-                alpha = 1.0f - __expf(-__ldg(sg + i) * dd.x);
-                d1 = dd.y;
-                c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
-            }
-            const float p_incl = warp_incl_prod(1.0f - alpha, lane);
-            float p_excl = __shfl_up_sync(FULL, p_incl, 1);
-            if (lane == 0) p_excl = 1.0f;
-            const float t_i = t_acc + warp_incl_sum(d1, lane);
-            const float T_after = T * p_incl;
-            const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
-            const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;       // last lane that still contributes
-            if (valid && lane <= last) {
-                const float w = alpha * (T * p_excl);
-                pr = fmaf(w, c0, pr); pg = fmaf(w, c1, pg); pb = fmaf(w, c2, pb);
-                pws += w;
-                pd = fmaf(w, t_i, pd);
-            }
-            if (term) break;
-            T = T * __shfl_sync(FULL, p_incl, 31);
-            t_acc = __shfl_sync(FULL, t_i, 31);
+    const uint32_t gl = lane & (G - 1u), gbase = lane - gl;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) / G;        // one group per row of the rays table
+    const bool have_ray = n < N;
+    uint32_t index = 0, offset = 0, cnt = 0;
+    if (have_ray) { index = rays[n * 3]; offset = rays[n * 3 + 1]; cnt = rays[n * 3 + 2]; }
+    const bool ok = have_ray && cnt != 0 && offset + cnt <= M;            // empty / dropped ray: outputs stay 0
+    const float* __restrict__ sg = sigmas + offset;
+    const float* __restrict__ cl = rgbs + (size_t)offset * 3;
+    const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
+    float T = 1.0f, t_acc = 0.f;
+    float pr = 0, pg = 0, pb = 0, pws = 0, pd = 0;                       // per-lane partial sums
+    bool done = !ok;
+    for (uint32_t base = 0;; base += G) {
+        const bool mine = !done && base < cnt;
+        if (!__any_sync(FULL, mine)) break;                              // warp-uniform: every group of the warp is finished
+        const uint32_t i = base + gl;
+        const bool valid = mine && i < cnt;
+        float alpha = 0.f, d1 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        if (valid) {
+            const float2 dd = __ldg(dl + i);
+            alpha = 1.0f - __expf(-__ldg(sg + i) * dd.x);
+            d1 = dd.y;
+            c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
         }
-        r = warp_sum(pr); g = warp_sum(pg); b = warp_sum(pb); ws = warp_sum(pws); d = warp_sum(pd);
+        const float p_incl = grp_incl_prod<G>(1.0f - alpha, gl);
+        float p_excl = __shfl_up_sync(FULL, p_incl, 1, G);
+        if (gl == 0) p_excl = 1.0f;
+        const float t_i = t_acc + grp_incl_sum<G>(d1, gl);
+        const float T_after = T * p_incl;
+        const uint32_t term = (__ballot_sync(FULL, valid && (T_after < T_thresh)) >> gbase) & GMASK;
+        const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : (uint32_t)(G - 1);   // last lane of the group that still contributes
+        if (valid && gl <= last) {
+            const float w = alpha * (T * p_excl);
+            pr = fmaf(w, c0, pr); pg = fmaf(w, c1, pg); pb = fmaf(w, c2, pb);
+            pws += w;
+            pd = fmaf(w, t_i, pd);
+        }
+        const float p_last = __shfl_sync(FULL, p_incl, G - 1, G), t_last = __shfl_sync(FULL, t_i, G - 1, G);
+        if (mine) {
+            if (term) done = true;
+            else { T = T * p_last; t_acc = t_last; }
+        }
     }
-    if (lane == 0) {
+    const float r = grp_sum<G>(pr), g = grp_sum<G>(pg), b = grp_sum<G>(pb), ws = grp_sum<G>(pws), d = grp_sum<G>(pd);
+    if (gl == 0 && have_ray) {
         weights_sum[index] = ws; depth[index] = d;
         image[index * 3] = r; image[index * 3 + 1] = g; image[index * 3 + 2] = b;
         if (mse.target) {
@@ -431,6 +459,7 @@ __global__ void k_step_counter_push(int* __restrict__ ring, const int* __restric
     nsteps[0] += 1;
 }
 
+template <int G>
 __global__ void __launch_bounds__(128)
 k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* __restrict__ grad_image,
                       const float* __restrict__ sigmas, const float* __restrict__ rgbs,
@@ -438,49 +467,61 @@ k_composite_train_bwd(const float* __restrict__ grad_weights_sum, const float* _
                       const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M,
                       uint32_t N, float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t GMASK = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per ray
-    if (n >= N) return;
-    const uint32_t index = rays[n * 3], offset = rays[n * 3 + 1], cnt = rays[n * 3 + 2];
-    if (cnt == 0 || offset + cnt > M) return;
-    const float gws = __ldg(grad_weights_sum + index);
-    const float gr = __ldg(grad_image + index * 3), gg = __ldg(grad_image + index * 3 + 1), gb = __ldg(grad_image + index * 3 + 2);
-    const float r_final = __ldg(image + index * 3), g_final = __ldg(image + index * 3 + 1), b_final = __ldg(image + index * 3 + 2);
-    const float ws_term = gws * (1 - __ldg(weights_sum + index));
+    const uint32_t gl = lane & (G - 1u), gbase = lane - gl;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) / G;        // one group per ray
+    const bool have_ray = n < N;
+    uint32_t index = 0, offset = 0, cnt = 0;
+    if (have_ray) { index = rays[n * 3]; offset = rays[n * 3 + 1]; cnt = rays[n * 3 + 2]; }
+    const bool ok = have_ray && cnt != 0 && offset + cnt <= M;
+    float gws = 0.f, gr = 0.f, gg = 0.f, gb = 0.f, r_final = 0.f, g_final = 0.f, b_final = 0.f, ws_term = 0.f;
+    if (ok) {
+        gws = __ldg(grad_weights_sum + index);
+        gr = __ldg(grad_image + index * 3); gg = __ldg(grad_image + index * 3 + 1); gb = __ldg(grad_image + index * 3 + 2);
+        r_final = __ldg(image + index * 3); g_final = __ldg(image + index * 3 + 1); b_final = __ldg(image + index * 3 + 2);
+        ws_term = gws * (1 - __ldg(weights_sum + index));
+    }
     const float* __restrict__ sg = sigmas + offset;
     const float* __restrict__ cl = rgbs + (size_t)offset * 3;
     const float2* __restrict__ dl = reinterpret_cast<const float2*>(deltas) + offset;
     float* __restrict__ gs = grad_sigmas + offset;
     float* __restrict__ gc = grad_rgbs + (size_t)offset * 3;
     float T = 1.0f, r_acc = 0.f, g_acc = 0.f, b_acc = 0.f;
-    for (uint32_t base = 0; base < cnt; base += 32) {
-        const uint32_t i = base + lane;
-        const bool valid = i < cnt;
+    bool done = !ok;
+    for (uint32_t base = 0;; base += G) {
+        const bool mine = !done && base < cnt;
+        if (!__any_sync(FULL, mine)) break;
+        const uint32_t i = base + gl;
+        const bool valid = mine && i < cnt;
         float alpha = 0.f, d0 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
         if (valid) {
             d0 = __ldg(dl + i).x;
             alpha = 1.0f - __expf(-__ldg(sg + i) * d0);
             c0 = __ldg(cl + i * 3); c1 = __ldg(cl + i * 3 + 1); c2 = __ldg(cl + i * 3 + 2);
         }
-        const float p_incl = warp_incl_prod(1.0f - alpha, lane);
-        float p_excl = __shfl_up_sync(FULL, p_incl, 1);
-        if (lane == 0) p_excl = 1.0f;
+        const float p_incl = grp_incl_prod<G>(1.0f - alpha, gl);
+        float p_excl = __shfl_up_sync(FULL, p_incl, 1, G);
+        if (gl == 0) p_excl = 1.0f;
         const float w = alpha * (T * p_excl);
         const float T_after = T * p_incl;
         // colour accumulated up to and including sample i
-        const float r_i = r_acc + warp_incl_sum(w * c0, lane);
-        const float g_i = g_acc + warp_incl_sum(w * c1, lane);
-        const float b_i = b_acc + warp_incl_sum(w * c2, lane);
-        const uint32_t term = __ballot_sync(FULL, valid && (T_after < T_thresh));
-        const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : 31u;
-        if (valid && lane <= last) {
+        const float r_i = r_acc + grp_incl_sum<G>(w * c0, gl);
+        const float g_i = g_acc + grp_incl_sum<G>(w * c1, gl);
+        const float b_i = b_acc + grp_incl_sum<G>(w * c2, gl);
+        const uint32_t term = (__ballot_sync(FULL, valid && (T_after < T_thresh)) >> gbase) & GMASK;
+        const uint32_t last = term ? (uint32_t)(__ffs(term) - 1) : (uint32_t)(G - 1);
+        if (valid && gl <= last) {
             gc[i * 3] = gr * w; gc[i * 3 + 1] = gg * w; gc[i * 3 + 2] = gb * w;
             gs[i] = d0 * (gr * (T_after * c0 - (r_final - r_i)) + gg * (T_after * c1 - (g_final - g_i)) +
                           gb * (T_after * c2 - (b_final - b_i)) + ws_term);
         }
-        if (term) break;
-        T = T * __shfl_sync(FULL, p_incl, 31);
-        r_acc = __shfl_sync(FULL, r_i, 31); g_acc = __shfl_sync(FULL, g_i, 31); b_acc = __shfl_sync(FULL, b_i, 31);
+        const float p_last = __shfl_sync(FULL, p_incl, G - 1, G);
+        const float r_last = __shfl_sync(FULL, r_i, G - 1, G), g_last = __shfl_sync(FULL, g_i, G - 1, G), b_last = __shfl_sync(FULL, b_i, G - 1, G);
+        if (mine) {
+            if (term) done = true;
+            else { T = T * p_last; r_acc = r_last; g_acc = g_last; b_acc = b_last; }
+        }
     }
 }
 
@@ -688,6 +729,23 @@ using namespace ngp;
         return check_launch(NAME);                                                     \
     } while (0)
 
+// training compositor: lanes per ray (NGP_COMPOSITE_GROUP = 8 | 16 | 32, default 8; 32 = one warp per ray, the round-1 form)
+static int composite_group() {
+    static const int g = [] { const char* e = getenv("NGP_COMPOSITE_GROUP"); const int v = e ? atoi(e) : 8; return (v == 16 || v == 32) ? v : 8; }();
+    return g;
+}
+#define NGP_LAUNCH_COMPOSITE(KERNEL, NAME, ...)                                                                        \
+    do {                                                                                                               \
+        if (N == 0) return NGP_OK;                                                                                     \
+        const int grp = composite_group();                                                                             \
+        if ((uint64_t)N * (uint64_t)grp > 0xffffffffull) return fail(NGP_EINVAL, NAME ": too many rays");             \
+        const uint32_t blocks = div_up(N * (uint32_t)grp, 128u);                                                       \
+        if (grp == 8) KERNEL<8><<<blocks, 128, 0, as_stream(stream)>>>(__VA_ARGS__);                                   \
+        else if (grp == 16) KERNEL<16><<<blocks, 128, 0, as_stream(stream)>>>(__VA_ARGS__);                            \
+        else KERNEL<32><<<blocks, 128, 0, as_stream(stream)>>>(__VA_ARGS__);                                           \
+        return check_launch(NAME);                                                                                     \
+    } while (0)
+
 extern "C" int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
                                       float min_near, float* nears, float* fars, ngp_stream_t stream) {
     NGP_LAUNCH_1D(k_near_far, N, 128, "near_far_from_aabb", rays_o, rays_d, aabb, N, min_near, nears, fars);
@@ -721,8 +779,8 @@ extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float
                                                 float* weights_sum, float* depth, float* image,
                                                 ngp_stream_t stream) {
     if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_forward: too many rays");
-    NGP_LAUNCH_1D(k_composite_train_fwd, N * 32, 128, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
-                  T_thresh, weights_sum, depth, image, MseArgs{});
+    NGP_LAUNCH_COMPOSITE(k_composite_train_fwd, "composite_rays_train_forward", sigmas, rgbs, deltas, rays, M, N,
+                         T_thresh, weights_sum, depth, image, MseArgs{});
 }
 // Compositor + loss head in one launch (extension used by the step driver): additionally forms pred = image + (1 - ws) * bg,
 // the squared error per ray (sqerr [N], row order of `rays`) and d(loss * *scale)/d(image, ws) for loss = sum(sqerr) * inv_norm / 2,
@@ -735,8 +793,8 @@ extern "C" int ngp_composite_rays_train_forward_mse(const float* sigmas, const f
     if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_forward_mse: too many rays");
     if (!target || !scale || !g_image || !g_ws || !sqerr) return fail(NGP_EINVAL, "composite_rays_train_forward_mse: null pointer");
     MseArgs mse{target, bg, inv_norm, scale, g_image, g_ws, sqerr};
-    NGP_LAUNCH_1D(k_composite_train_fwd, N * 32, 128, "composite_rays_train_forward_mse", sigmas, rgbs, deltas, rays, M, N,
-                  T_thresh, weights_sum, depth, image, mse);
+    NGP_LAUNCH_COMPOSITE(k_composite_train_fwd, "composite_rays_train_forward_mse", sigmas, rgbs, deltas, rays, M, N,
+                         T_thresh, weights_sum, depth, image, mse);
 }
 // ring [1] i32 (next row), counter [2] i32 (this march's totals), nsteps [1] i32, step_counter [16,2] i32
 extern "C" int ngp_step_counter_push(int32_t* ring, const int32_t* counter, int32_t* nsteps, int32_t* step_counter,
@@ -751,8 +809,8 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, 
                                                  uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
                                                  float* grad_rgbs, ngp_stream_t stream) {
     if ((uint64_t)N * 32 > 0xffffffffull) return fail(NGP_EINVAL, "composite_rays_train_backward: too many rays");
-    NGP_LAUNCH_1D(k_composite_train_bwd, N * 32, 128, "composite_rays_train_backward", grad_weights_sum, grad_image, sigmas,
-                  rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    NGP_LAUNCH_COMPOSITE(k_composite_train_bwd, "composite_rays_train_backward", grad_weights_sum, grad_image, sigmas,
+                         rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
 }
 extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
                               const float* rays_o, const float* rays_d, float bound, float dt_gamma,

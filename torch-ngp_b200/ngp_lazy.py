@@ -51,12 +51,15 @@ class Deferred(torch.Tensor):
 
     @staticmethod
     def _wrap(cls, shape, dtype, device):
-        return torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=dtype, device=device, requires_grad=False)
+        t = torch.Tensor._make_wrapper_subclass(cls, tuple(shape), dtype=dtype, device=device, requires_grad=False)
+        t._grad_mode = torch.is_grad_enabled()       # the producing call's grad mode travels with the tensor, like its autocast state
+        return t
 
     def materialize(self):
-        """The eager op, run under the autocast state the producing module saw (the consumer may sit outside the autocast region)."""
+        """The eager op, run under the autocast state AND the grad mode the producing module saw (the consumer may sit outside the
+        `autocast` / `no_grad` region: `with torch.no_grad(): f = encoder(x)` followed by `f.float()` must not build a graph)."""
         if self._value is None:
-            with torch.autocast('cuda', dtype=torch.half, enabled=True):
+            with torch.autocast('cuda', dtype=torch.half, enabled=True), torch.set_grad_enabled(getattr(self, "_grad_mode", True)):
                 self._value = self._compute()
         return self._value
 
@@ -214,7 +217,8 @@ def grid_mlp(lazy, mlp):
     """FFMLP.forward's hook for a DeferredGridFeatures input; returns None when the fused kernel does not cover the configuration."""
     enc = lazy._encoder
     if not (enabled and lazy._value is None and mlp.hidden_dim == 64 and mlp.activation == 0 and mlp.output_activation == 6
-            and mlp.input_dim == enc.output_dim and mlp.padded_output_dim == 16 and 2 <= mlp.num_layers <= 5):
+            and mlp.input_dim == enc.output_dim and mlp.padded_output_dim == 16 and 2 <= mlp.num_layers <= 5
+            and getattr(lazy, "_grad_mode", True) == torch.is_grad_enabled()):       # producer under no_grad, consumer not: eager semantics
         return None
     inference = not (mlp.training and torch.is_grad_enabled())
     cfg = (float(lazy._bound), float(enc.per_level_scale), int(enc.base_resolution), enc.gridtype_id, bool(enc.align_corners),
@@ -282,7 +286,7 @@ def color_mlp(lazy, mlp):
     geo = lazy._geo
     if not (enabled and lazy._value is None and mlp.hidden_dim == 64 and mlp.activation == 0 and mlp.output_activation == 6
             and mlp.input_dim == 32 and mlp.padded_output_dim == 16 and mlp.output_dim == 3 and 2 <= mlp.num_layers <= 5
-            and _rows_of_16(geo) is not None):
+            and _rows_of_16(geo) is not None and getattr(lazy, "_grad_mode", True) == torch.is_grad_enabled()):
         return None
     inference = not (mlp.training and torch.is_grad_enabled())
     return _ColorMLPFn.apply(lazy._sh._dirs, geo, lazy._pad, mlp.weights, (mlp.num_layers, mlp.output_dim, inference))
