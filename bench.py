@@ -587,7 +587,9 @@ def main():
             traffic = t["dram_bytes_per_sample"] * dd["units"] / dd["calls"]
     roof.update({"traffic": traffic, "traffic_source": (os.path.relpath(tpath, ROOT) + " (ncu --set full, per-sample x samples/launch)") if traffic else None,
                  "peak_source": pk["src"], "avg_launch_ms": per_launch_ms,
-                 "share_of_step": dd["ms"] / ms_eager, "algorithmic_bytes_per_launch": dd["bytes"] / dd["calls"]})
+                 "share_of_step": dd["ms"] / ms_eager, "algorithmic_bytes_per_launch": dd["bytes"] / dd["calls"],
+                 "units_per_launch": dd["units"] / dd["calls"],
+                 "units_note": "sample rows of the padded steady-state budget M (mean_count rounded up to 128; pad rows are zero-filled and still gather / scatter), not only the rows a ray produced"})
     launches = launches // 1      # launches of OUR kernels per timed region (counted in the eager pass; a graph replays the same set)
     breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
                      "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None,
